@@ -1,0 +1,95 @@
+/* include/mirage_b200.h
+ *
+ * C ABI of libmirage_b200.so -- the B200 (sm_100a) kernels behind the MIRAGE MultiViT hot path.
+ *
+ * The reference (j-morano/MIRAGE) has no FFI of its own: every op on this path is a PyTorch
+ * library call.  Each entry point below therefore cites the reference call site (file:line under
+ * the reference checkout) whose arithmetic it replaces.  The host side (mirage_b200/*.py) binds
+ * these with ctypes and exposes the reference's own nn.Module API on top.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on failure; mb_last_error() then holds
+ *     a human-readable message (thread-local).
+ *   - all pointers are DEVICE pointers unless stated otherwise; nothing is allocated inside.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised.
+ *   - row-major tensors; "ld" arguments are leading dimensions in ELEMENTS.
+ *   - bf16 = __nv_bfloat16 bit pattern (uint16_t), f32 = float, i64 = int64_t.
+ */
+#ifndef MIRAGE_B200_H_
+#define MIRAGE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_VERSION 1
+
+/* ---------------------------------------------------------------- runtime ------------------ */
+const char* mb_last_error(void);
+int mb_version(void);
+int mb_sm_count(void);
+void mb_clear_tensor_map_cache(void);
+
+/* ---------------------------------------------------------------- GEMM --------------------- */
+/* One tcgen05/TMEM GEMM with fused epilogues:  D[M,N] = epilogue( A[M,K] * B[N,K]^T ).
+ *
+ * Replaces every nn.Linear / patch-embedding Conv2d on the path and their backward GEMMs:
+ *   Attention.qkv / .proj        mirage/utils.py:177-186
+ *   Mlp.fc1 (+GELU) / .fc2       mirage/utils.py:155-157
+ *   CrossAttention.q/.kv/.proj   mirage/utils.py:209-221
+ *   proj_context / out_proj      mirage/output_adapters.py:272,288
+ *   PatchedInputAdapter.proj     mirage/input_adapters.py:101   (a_layout = MB_A_PATCH32)
+ *   SemSegInputAdapter.proj      mirage/input_adapters.py:229
+ *
+ * Operand layouts ("major" = which dimension is contiguous in memory):
+ *   MB_MAJOR_K   A is [M, K] with K contiguous (lda = row stride).   B is [N, K], K contiguous.
+ *   MB_MAJOR_MN  A is [K, M] with M contiguous (lda = row stride).   B is [K, N], N contiguous.
+ * so   forward  y = x W^T      : A=x   (K-major),  B=W  (K-major)
+ *      dgrad    dx = dy W      : A=dy  (K-major),  B=W  (MN-major, reduction over W's rows)
+ *      wgrad    dW = dy^T x    : A=dy  (MN-major), B=x  (MN-major), k_splits > 1 allowed.
+ *   MB_A_PATCH32: A is an fp32 image batch [B, 1, H, W]; row m = (b, nh, nw) is the 32x32 patch,
+ *      K = 1024 in (ph, pw) order; loaded patch-row by patch-row with a 5-D TMA box (no im2col).
+ *      Requires in_dtype = MB_F32 (tf32 tensor-core math), (W/32) dividing 128.
+ *
+ * Epilogue, applied in this order on the fp32 accumulator acc[m, n]:
+ *   1. if bias:            acc += bias[n]                                   (f32 [N])
+ *   2. if MB_EPI_GELU:     (aux_out ? aux_out[m,n] = bf16(acc) : -);  acc = gelu_erf(acc)
+ *   3. if MB_EPI_DGELU:    acc *= gelu_erf'(aux_in[m,n])                     (bf16 [M, ld_aux])
+ *   4. if residual:        acc += residual[(res_period ? m % res_period : m), n]   (f32, ld_res)
+ *   5. store: out_dtype MB_BF16 or MB_F32 at out[m * ldc + n];  with MB_EPI_ATOMIC (required when
+ *      k_splits > 1) the store is an fp32 atomic add into a pre-zeroed (or accumulating) buffer.
+ */
+enum { MB_BF16 = 0, MB_F32 = 1 };
+enum { MB_MAJOR_K = 0, MB_MAJOR_MN = 1, MB_A_PATCH32 = 2 };
+enum { MB_EPI_GELU = 1, MB_EPI_DGELU = 2, MB_EPI_ATOMIC = 4 };
+
+typedef struct mb_gemm_args {
+  const void* a;      /* bf16 (or f32 when in_dtype == MB_F32) */
+  const void* b;      /* same dtype as a */
+  void* out;          /* bf16 or f32, see out_dtype */
+  const float* bias;  /* f32 [N] or NULL */
+  const float* residual; /* f32 or NULL */
+  const void* aux_in; /* bf16 [M, ld_aux] pre-activation, MB_EPI_DGELU only */
+  void* aux_out;      /* bf16 [M, ld_aux] pre-activation copy, MB_EPI_GELU only, may be NULL */
+  int64_t m, n, k;
+  int64_t lda, ldb, ldc, ld_res, ld_aux;
+  int64_t res_period; /* 0 = residual indexed by m */
+  int32_t a_layout;   /* MB_MAJOR_K | MB_MAJOR_MN | MB_A_PATCH32 */
+  int32_t b_layout;   /* MB_MAJOR_K | MB_MAJOR_MN */
+  int32_t in_dtype;   /* MB_BF16 | MB_F32 (tf32 math) */
+  int32_t out_dtype;  /* MB_BF16 | MB_F32 */
+  int32_t epilogue;   /* bitmask of MB_EPI_* */
+  int32_t k_splits;   /* >= 1 */
+  int32_t block_n;    /* 0 = auto, else 64 / 128 / 256 */
+  int32_t img_h, img_w; /* MB_A_PATCH32 only */
+} mb_gemm_args;
+
+int mb_gemm(const mb_gemm_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MIRAGE_B200_H_ */

@@ -1,0 +1,90 @@
+"""ctypes binding of libmirage_b200.so (see include/mirage_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libmirage_b200.so"
+
+# enums mirrored from include/mirage_b200.h
+MB_BF16, MB_F32 = 0, 1
+MB_MAJOR_K, MB_MAJOR_MN, MB_A_PATCH32 = 0, 1, 2
+MB_EPI_GELU, MB_EPI_DGELU, MB_EPI_ATOMIC = 1, 2, 4
+
+
+class MirageB200Error(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("b", C.c_void_p), ("out", C.c_void_p),
+        ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("aux_in", C.c_void_p), ("aux_out", C.c_void_p),
+        ("m", C.c_int64), ("n", C.c_int64), ("k", C.c_int64),
+        ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
+        ("ld_res", C.c_int64), ("ld_aux", C.c_int64),
+        ("res_period", C.c_int64),
+        ("a_layout", C.c_int32), ("b_layout", C.c_int32),
+        ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
+        ("epilogue", C.c_int32), ("k_splits", C.c_int32), ("block_n", C.c_int32),
+        ("img_h", C.c_int32), ("img_w", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def _declare(lib):
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.mb_last_error.restype = C.c_char_p
+    lib.mb_last_error.argtypes = []
+    lib.mb_version.restype = C.c_int
+    lib.mb_sm_count.restype = C.c_int
+    lib.mb_clear_tensor_map_cache.restype = None
+    lib.mb_gemm.restype = C.c_int
+    lib.mb_gemm.argtypes = [C.POINTER(GemmArgs), vp]
+    # the remaining entry points are declared by signature table so the loader and the symbol
+    # test (tests/test_abi.py) share one source of truth
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
+
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> argtypes (all return int).  Filled in as kernels are added; order matches the header.
+SIGNATURES: dict[str, list] = {}
+
+# every symbol include/mirage_b200.h declares
+EXPORTED = ["mb_last_error", "mb_version", "mb_sm_count", "mb_clear_tensor_map_cache", "mb_gemm"]
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise MirageB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m mirage_b200.build` "
+                "(there is no CPU or PyTorch fallback for the MIRAGE hot path)")
+        handle = C.CDLL(str(LIB_PATH), mode=os.RTLD_NOW | os.RTLD_LOCAL)
+        _declare(handle)
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().mb_last_error().decode(errors="replace")
+        raise MirageB200Error(f"{what} failed (rc={rc}): {msg}")
+
+
+def exported_symbols():
+    return list(EXPORTED) + list(SIGNATURES.keys())

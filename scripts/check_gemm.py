@@ -1,0 +1,193 @@
+"""GPU bring-up check for mb_gemm: run `python scripts/check_gemm.py <group>` on a B200.
+
+Each group runs in its own process (a trapped kernel poisons the CUDA context), prints a verdict
+per case and a short diagnosis of the error pattern when a case fails.
+"""
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from mirage_b200 import _lib as L  # noqa: E402
+from mirage_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+
+
+def report(name, got, ref, tol=2e-2):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    scale = ref.abs().max().item() + 1e-9
+    rel = err.max().item() / scale
+    bad = err > tol * scale
+    ok = rel <= tol and torch.isfinite(got).all().item()
+    print(f"[{'PASS' if ok else 'FAIL'}] {name}: max_rel={rel:.3e} bad_frac={bad.float().mean().item():.4f}",
+          flush=True)
+    if not ok:
+        idx = bad.nonzero()
+        if idx.numel():
+            rows = idx[:, 0].unique()
+            cols = idx[:, 1].unique()
+            print(f"    bad rows: n={rows.numel()} first={rows[:12].tolist()}  "
+                  f"bad cols: n={cols.numel()} first={cols[:12].tolist()}")
+            r, c = idx[0].tolist()
+            print(f"    first bad ({r},{c}): got={got[r, c].item():.5f} ref={ref[r, c].item():.5f}")
+            print(f"    got[0,:8]={got[0, :8].tolist()}\n    ref[0,:8]={ref[0, :8].tolist()}")
+    return ok
+
+
+def mk(m, k, dtype=torch.bfloat16, scale=1.0):
+    return (torch.randn(m, k, device=dev) * scale).to(dtype)
+
+
+def case_fwd(m, n, k, bn=0, **kw):
+    a = mk(m, k)
+    w = mk(n, k, scale=k ** -0.5)
+    out = ops.gemm(a, w, m=m, n=n, k=k, block_n=bn, **kw)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    return report(f"fwd KK m={m} n={n} k={k} bn={bn}", out, ref)
+
+
+def group_basic():
+    ok = True
+    ok &= case_fwd(128, 64, 64, bn=64)
+    ok &= case_fwd(128, 128, 64, bn=128)
+    ok &= case_fwd(128, 256, 64, bn=256)
+    ok &= case_fwd(128, 256, 256, bn=256)
+    ok &= case_fwd(256, 512, 1024, bn=256)
+    ok &= case_fwd(4096, 1024, 1024, bn=256)
+    ok &= case_fwd(4096, 1024, 1024, bn=128)
+    ok &= case_fwd(4096, 1024, 1024, bn=64)
+    ok &= case_fwd(1539, 832, 256)       # ragged M and N
+    ok &= case_fwd(99 * 7, 768, 768)
+    ok &= case_fwd(131328, 1024, 1024)   # full cfg-2 row count, many tiles per CTA
+    return ok
+
+
+def group_epilogue():
+    ok = True
+    m, n, k = 1000, 512, 256
+    a, w = mk(m, k), mk(n, k, scale=k ** -0.5)
+    bias = torch.randn(n, device=dev)
+    res = torch.randn(m, n, device=dev)
+    base = a.float() @ w.float().t()
+    out = ops.gemm(a, w, m=m, n=n, k=k, bias=bias)
+    ok &= report("bias", out, base + bias)
+    out = ops.gemm(a, w, m=m, n=n, k=k, bias=bias, out_dtype=torch.float32)
+    ok &= report("bias f32 out", out, base + bias, tol=5e-3)
+    pre = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+    out = ops.gemm(a, w, m=m, n=n, k=k, bias=bias, gelu=True, aux_out=pre)
+    ok &= report("bias+gelu", out, torch.nn.functional.gelu(base + bias))
+    ok &= report("gelu aux_out", pre, base + bias)
+    out = ops.gemm(a, w, m=m, n=n, k=k, bias=bias, residual=res, out_dtype=torch.float32)
+    ok &= report("bias+residual f32", out, base + bias + res, tol=5e-3)
+    # in-place residual
+    x = res.clone()
+    ops.gemm(a, w, m=m, n=n, k=k, bias=bias, residual=x, out=x)
+    ok &= report("bias+residual in place", x, base + bias + res, tol=5e-3)
+    pos = torch.randn(250, n, device=dev)
+    out = ops.gemm(a, w, m=m, n=n, k=k, bias=bias, residual=pos, res_period=250,
+                   out_dtype=torch.float32)
+    ok &= report("bias+periodic residual", out, base + bias + pos.repeat(4, 1), tol=5e-3)
+    h = mk(m, n)
+    out = ops.gemm(a, w, m=m, n=n, k=k, dgelu_aux=h)
+    hf = h.float().requires_grad_(True)
+    g = torch.autograd.grad(torch.nn.functional.gelu(hf).sum(), hf)[0]
+    ok &= report("dgelu", out, base * g)
+    return ok
+
+
+def group_dgrad():
+    ok = True
+    for (m, n_out, k_in, bn) in [(128, 64, 64, 64), (128, 64, 256, 256), (256, 128, 128, 128),
+                                 (1000, 768, 512, 0), (4096, 4096, 1024, 0)]:
+        dy = mk(m, n_out)
+        w = mk(n_out, k_in, scale=n_out ** -0.5)
+        # dx[m, k_in] = dy[m, n_out] @ w[n_out, k_in]; reduction over n_out; B = w is MN-major
+        out = ops.gemm(dy, w, m=m, n=k_in, k=n_out, b_layout=L.MB_MAJOR_MN, block_n=bn)
+        ok &= report(f"dgrad m={m} n_out={n_out} k_in={k_in} bn={bn}", out, dy.float() @ w.float())
+    return ok
+
+
+def group_wgrad():
+    ok = True
+    for (t, n_out, k_in, bn, splits) in [(64, 128, 64, 64, 1), (64, 128, 256, 256, 1),
+                                         (256, 256, 256, 128, 1), (1000, 768, 512, 0, 1),
+                                         (4096, 1024, 1024, 0, 8), (25344, 1024, 4096, 0, 4)]:
+        dy = mk(t, n_out, scale=t ** -0.5)
+        x = mk(t, k_in)
+        out = torch.zeros(n_out, k_in, device=dev)
+        # dw[n_out, k_in] = dy^T @ x; reduction over tokens; both operands MN-major
+        ops.gemm(dy, x, m=n_out, n=k_in, k=t, a_layout=L.MB_MAJOR_MN, b_layout=L.MB_MAJOR_MN,
+                 out=out, block_n=bn, k_splits=splits, atomic=True)
+        ok &= report(f"wgrad t={t} n_out={n_out} k_in={k_in} bn={bn} splits={splits}", out,
+                     dy.float().t() @ x.float(), tol=1e-2)
+    return ok
+
+
+def group_patch():
+    ok = True
+    for (b, d) in [(1, 256), (3, 768), (8, 1024)]:
+        img = torch.rand(b, 1, 512, 512, device=dev)
+        w = torch.randn(d, 1, 32, 32, device=dev) * 0.03
+        bias = torch.randn(d, device=dev) * 0.1
+        pos = torch.randn(256, d, device=dev)
+        out = ops.gemm(img, w.view(d, 1024), m=b * 256, n=d, k=1024, a_layout=L.MB_A_PATCH32,
+                       img_hw=(512, 512), bias=bias, residual=pos, res_period=256,
+                       out_dtype=torch.float32)
+        ref = torch.nn.functional.conv2d(img, w, bias, stride=32).flatten(2).transpose(1, 2) + pos
+        ok &= report(f"patch32 tf32 b={b} d={d}", out.view(b, 256, d).flatten(0, 1), ref.flatten(0, 1),
+                     tol=5e-3)
+    # plain tf32 K-major GEMM
+    a = torch.randn(300, 512, device=dev)
+    w = torch.randn(256, 512, device=dev) * 0.05
+    out = ops.gemm(a, w, m=300, n=256, k=512, out_dtype=torch.float32)
+    ok &= report("tf32 KK", out, a @ w.t(), tol=5e-3)
+    return ok
+
+
+def group_perf():
+    shapes = [(131328, 3072, 1024), (131328, 1024, 1024), (131328, 4096, 1024), (131328, 1024, 4096),
+              (25344, 4096, 1024), (8192, 8192, 8192)]
+    for (m, n, k) in shapes:
+        a, w = mk(m, k), mk(n, k, scale=k ** -0.5)
+        bias = torch.randn(n, device=dev)
+        out = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+        for _ in range(3):
+            ops.gemm(a, w, m=m, n=n, k=k, bias=bias, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 10
+        e0.record()
+        for _ in range(iters):
+            ops.gemm(a, w, m=m, n=n, k=k, bias=bias, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        tf = 2.0 * m * n * k / ms / 1e9
+        for _ in range(3):
+            torch.nn.functional.linear(a, w)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            torch.nn.functional.linear(a, w)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_t = e0.elapsed_time(e1) / iters
+        print(f"[PERF] m={m} n={n} k={k}: mb_gemm {ms:.3f} ms = {tf:.0f} TFLOP/s | "
+              f"cuBLAS {ms_t:.3f} ms = {2.0 * m * n * k / ms_t / 1e9:.0f} TFLOP/s", flush=True)
+    return True
+
+
+if __name__ == "__main__":
+    grp = sys.argv[1]
+    t0 = time.time()
+    print(f"=== group {grp} on {torch.cuda.get_device_name(0)} ===", flush=True)
+    ok = globals()[f"group_{grp}"]()
+    torch.cuda.synchronize()
+    print(f"=== group {grp}: {'ALL PASS' if ok else 'FAILURES'} ({time.time() - t0:.1f}s) ===", flush=True)
+    sys.exit(0 if ok else 1)
