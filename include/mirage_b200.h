@@ -58,8 +58,11 @@ void mb_clear_tensor_map_cache(void);
  *   2. if MB_EPI_GELU:     (aux_out ? aux_out[m,n] = bf16(acc) : -);  acc = gelu_erf(acc)
  *   3. if MB_EPI_DGELU:    acc *= gelu_erf'(aux_in[m,n])                     (bf16 [M, ld_aux])
  *   4. if residual:        acc += residual[(res_period ? m % res_period : m), n]   (f32, ld_res)
- *   5. store: out_dtype MB_BF16 or MB_F32 at out[m * ldc + n];  with MB_EPI_ATOMIC (required when
- *      k_splits > 1) the store is an fp32 atomic add into a pre-zeroed (or accumulating) buffer.
+ *   5. store: out_dtype MB_BF16 or MB_F32 at out[r(m) * ldc + n];  with MB_EPI_ATOMIC (required
+ *      when k_splits > 1) the store is an fp32 atomic add into a pre-zeroed (or accumulating) buffer.
+ *      r(m) = m, or with out_row_period = P > 0:  r(m) = (m / P) * out_row_stride + m % P +
+ *      out_row_offset -- this lets each input adapter write its tokens straight into its slice of
+ *      the concatenated [B, N_all (+ global), D] token buffer (the torch.cat of model.py:384/:520).
  */
 enum { MB_BF16 = 0, MB_F32 = 1 };
 enum { MB_MAJOR_K = 0, MB_MAJOR_MN = 1, MB_A_PATCH32 = 2 };
@@ -84,9 +87,78 @@ typedef struct mb_gemm_args {
   int32_t k_splits;   /* >= 1 */
   int32_t block_n;    /* 0 = auto, else 64 / 128 / 256 */
   int32_t img_h, img_w; /* MB_A_PATCH32 only */
+  int64_t out_row_period, out_row_stride, out_row_offset; /* 0,0,0 = identity row map */
 } mb_gemm_args;
 
 int mb_gemm(const mb_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------- attention ---------------- */
+/* Fused softmax(Q K^T * scale) V, no mask, no dropout (the reference always runs attn_drop = 0).
+ * Replaces F.scaled_dot_product_attention AND the following .transpose(1, 2).reshape(B, N, C) copy:
+ *   Attention.forward        mirage/utils.py:181-185
+ *   CrossAttention.forward   mirage/utils.py:216-220
+ *
+ * q  : bf16, token-major: element (b, i, h, d) at q[(b*nq + i)*ldq + h*head_dim + d]
+ * k,v: bf16, same convention with nk / ldk / ldv.  (For the fused qkv Linear output [B*N, 3*D] pass
+ *      q = base, k = base + D, v = base + 2*D and ldq = ldk = ldv = 3*D.)
+ * out: bf16 [B*nq, ldo] with head h in columns [h*head_dim, (h+1)*head_dim) -- i.e. already in the
+ *      layout the output projection consumes.
+ * lse: optional f32 [B, heads, nq]: log-sum-exp of the scaled scores (saved for the backward pass).
+ * head_dim is 64 (encoder) or 32 (decoder).
+ */
+typedef struct mb_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  float* lse;
+  int64_t batch, heads, nq, nk;
+  int64_t ldq, ldk, ldv, ldo;
+  int32_t head_dim;
+  float scale;
+} mb_attn_args;
+
+int mb_attn_fwd(const mb_attn_args* args, void* stream);
+
+/* ---------------------------------------------------------------- row kernels (HBM-bound) -- */
+/* LayerNorm(eps) with affine, fp32 statistics.  nn.LayerNorm at mirage/utils.py:241,250,260-261,
+ * output_adapters.py:115-117, mirage_wrapper.py:201.
+ * x f32 [rows, ldx]; y bf16 or f32 [rows, ldy] (y_dtype); mean/rstd optional f32 [rows] (saved for
+ * the backward pass).  dim must be a multiple of 128, at most 1024. */
+int mb_layernorm_fwd(const float* x, const float* weight, const float* bias, void* y,
+                     int32_t y_dtype, float* mean, float* rstd, int64_t rows, int64_t dim,
+                     int64_t ldx, int64_t ldy, float eps, void* stream);
+
+/* LayerNorm backward.  dy bf16 or f32 (dy_dtype); dx f32 = LN'(dy) (+ dres if non-NULL: the gradient
+ * arriving through the residual branch); dweight/dbias f32 [dim], overwritten or accumulated.
+ * workspace: mb_layernorm_bwd_workspace(rows, dim) bytes of device memory. */
+int64_t mb_layernorm_bwd_workspace(int64_t rows, int64_t dim);
+int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* weight,
+                     const float* mean, const float* rstd, const float* dres, float* dx,
+                     float* dweight, float* dbias, int32_t accumulate, void* workspace,
+                     int64_t rows, int64_t dim, int64_t ldx, int64_t lddy, int64_t lddx,
+                     void* stream);
+
+/* out[c] (+)= sum_r a[r, c] -- bias gradient of every nn.Linear on the path. */
+int64_t mb_colsum_workspace(int64_t rows, int64_t cols);
+int mb_colsum(const void* a, int32_t a_dtype, float* out, int32_t accumulate, void* workspace,
+              int64_t rows, int64_t cols, int64_t lda, void* stream);
+
+/* Visible-token selection, mirage/model.py:384-391:
+ *   out[b, j, :]          = src[b, ids_keep[b, j], :]   j < n_keep      (bit-exact row copy)
+ *   out[b, n_keep + t, :] = global_tokens[t, :]                          (global tokens LAST)
+ * src f32 [B, n_src, dim], ids_keep i64 [B, n_keep], out f32 [B, n_keep + n_global, dim]. */
+int mb_token_gather_fwd(const float* src, const int64_t* ids_keep, const float* global_tokens,
+                        float* out, int64_t batch, int64_t n_src, int64_t n_keep, int64_t n_global,
+                        int64_t dim, void* stream);
+/* Backward: dsrc (zero-filled here) receives dout rows at ids_keep; dglobal[t] = sum_b dout[b, n_keep+t]. */
+int mb_token_gather_bwd(const float* dout, const int64_t* ids_keep, float* dsrc, float* dglobal,
+                        int64_t batch, int64_t n_src, int64_t n_keep, int64_t n_global, int64_t dim,
+                        void* stream);
+/* out[b, row_offset + t, :] = global_tokens[t, :] for the un-masked path (model.py:523-524). */
+int mb_fill_global_rows(const float* global_tokens, float* out, int64_t batch, int64_t rows_total,
+                        int64_t row_offset, int64_t n_global, int64_t dim, void* stream);
+int mb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,17 @@ class GemmArgs(C.Structure):
         ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
         ("epilogue", C.c_int32), ("k_splits", C.c_int32), ("block_n", C.c_int32),
         ("img_h", C.c_int32), ("img_w", C.c_int32),
+        ("out_row_period", C.c_int64), ("out_row_stride", C.c_int64), ("out_row_offset", C.c_int64),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("lse", C.c_void_p),
+        ("batch", C.c_int64), ("heads", C.c_int64), ("nq", C.c_int64), ("nk", C.c_int64),
+        ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
+        ("head_dim", C.c_int32), ("scale", C.c_float),
     ]
 
 
@@ -49,6 +60,11 @@ def _declare(lib):
     lib.mb_clear_tensor_map_cache.restype = None
     lib.mb_gemm.restype = C.c_int
     lib.mb_gemm.argtypes = [C.POINTER(GemmArgs), vp]
+    lib.mb_attn_fwd.restype = C.c_int
+    lib.mb_attn_fwd.argtypes = [C.POINTER(AttnArgs), vp]
+    for name in ("mb_layernorm_bwd_workspace", "mb_colsum_workspace"):
+        getattr(lib, name).restype = C.c_int64
+        getattr(lib, name).argtypes = [i64, i64]
     # the remaining entry points are declared by signature table so the loader and the symbol
     # test (tests/test_abi.py) share one source of truth
     for name, argtypes in SIGNATURES.items():
@@ -60,10 +76,20 @@ def _declare(lib):
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> argtypes (all return int).  Filled in as kernels are added; order matches the header.
-SIGNATURES: dict[str, list] = {}
+SIGNATURES: dict[str, list] = {
+    "mb_layernorm_fwd": [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp],
+    "mb_layernorm_bwd": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
+                         _i64, _i64, _i64, _i64, _i64, _vp],
+    "mb_colsum": [_vp, _i32, _vp, _i32, _vp, _i64, _i64, _i64, _vp],
+    "mb_token_gather_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
+    "mb_token_gather_bwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
+    "mb_fill_global_rows": [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
+    "mb_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
+}
 
 # every symbol include/mirage_b200.h declares
-EXPORTED = ["mb_last_error", "mb_version", "mb_sm_count", "mb_clear_tensor_map_cache", "mb_gemm"]
+EXPORTED = ["mb_last_error", "mb_version", "mb_sm_count", "mb_clear_tensor_map_cache", "mb_gemm",
+            "mb_attn_fwd", "mb_layernorm_bwd_workspace", "mb_colsum_workspace"]
 
 
 def lib():

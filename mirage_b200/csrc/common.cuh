@@ -284,6 +284,19 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+      "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
+      "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]),
+      "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]),
+      "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -303,17 +316,22 @@ __device__ __forceinline__ void tmem_st_wait() {
 //      is several slabs, each slab_bytes apart.
 //      LBO = slab_bytes (next 64 M/N), SBO = 1024 B (next group of 8 K rows).
 //      Advancing K by one UMMA_K (16 rows) = start address + 2048 B.
+//
+// The same holds for 64-byte swizzle (rows of 64 bytes, 8-row atoms of 512 bytes) with every
+// "128" above halved; it is used for head_dim = 32 attention operands.
 constexpr uint64_t kDescVersion1 = 1ull << 46;
 constexpr uint64_t kDescSwizzle128B = 2ull << 61;
+constexpr uint64_t kDescSwizzle64B = 4ull << 61;
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
+                                                   uint32_t sbo_bytes,
+                                                   uint64_t swizzle = kDescSwizzle128B) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= kDescVersion1;
-  d |= kDescSwizzle128B;
+  d |= swizzle;
   return d;
 }
 
@@ -356,6 +374,13 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// 2^x on the MUFU unit; ex2.approx(-inf) = +0
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -375,8 +400,10 @@ __device__ __forceinline__ float warp_max(float v) {
 enum TmaDtype { kTmaBF16 = 0, kTmaF32 = 1 };
 
 // dims / strides are innermost-first; strides_bytes has rank-1 entries (dim 1..rank-1).
+// swizzle_bytes: 128 (default) or 64.
 int make_tensor_map(CUtensorMap* out, const void* base, TmaDtype dtype, int rank,
-                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                    int swizzle_bytes = 128);
 
 int sm_count();
 

@@ -35,6 +35,9 @@ struct GemmDev {
   // MB_A_PATCH32
   int rows_per_img;  // tokens per image
   int grid_w;        // patches per image row
+  // output row map
+  int orow_period;
+  long long orow_stride, orow_offset;
 };
 
 constexpr int kGemmThreads = 384;
@@ -205,6 +208,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const bool add_bias = (p.bias != nullptr) && (split == 0);
       const long long res_row =
           p.residual ? (long long)(p.res_period > 0 ? row % p.res_period : row) : 0;
+      const long long orow =
+          p.orow_period > 0
+              ? (long long)(row / p.orow_period) * p.orow_stride + row % p.orow_period + p.orow_offset
+              : (long long)row;
 
       mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
@@ -261,11 +268,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
             }
             if (p.epilogue & MB_EPI_ATOMIC) {
-              float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col;
+              float* o = reinterpret_cast<float*>(p.out) + orow * p.ldc + col;
 #pragma unroll
               for (int i = 0; i < 8; ++i) atomicAdd(o + i, f[i]);
             } else if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldc + col;
+              float* o = reinterpret_cast<float*>(p.out) + orow * p.ldc + col;
               *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
               *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
             } else {
@@ -275,7 +282,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               pk.z = pack_bf16x2(f[4], f[5]);
               pk.w = pack_bf16x2(f[6], f[7]);
               __nv_bfloat16* o =
-                  reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldc + col;
+                  reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + col;
               *reinterpret_cast<uint4*>(o) = pk;
             }
           }
@@ -389,6 +396,9 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
   p.total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
   p.rows_per_img = 0;
   p.grid_w = 0;
+  p.orow_period = (int)a->out_row_period;
+  p.orow_stride = a->out_row_stride;
+  p.orow_offset = a->out_row_offset;
 
   CUtensorMap ta, tb;
   const TmaDtype tdt = tf32 ? kTmaF32 : kTmaBF16;

@@ -75,14 +75,18 @@ static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 
 int make_tensor_map(CUtensorMap* out, const void* base, TmaDtype dtype, int rank,
-                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                    int swizzle_bytes) {
   MB_REQUIRE(rank >= 1 && rank <= 5, "make_tensor_map: rank %d unsupported", rank);
   MB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0,
              "make_tensor_map: base pointer %p is not 16-byte aligned", base);
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.w[0] = reinterpret_cast<uint64_t>(base);
-  key.w[1] = (static_cast<uint64_t>(dtype) << 8) | static_cast<uint64_t>(rank);
+  key.w[1] = (static_cast<uint64_t>(swizzle_bytes) << 16) | (static_cast<uint64_t>(dtype) << 8) |
+             static_cast<uint64_t>(rank);
+  MB_REQUIRE(swizzle_bytes == 128 || swizzle_bytes == 64, "make_tensor_map: swizzle %d unsupported",
+             swizzle_bytes);
   for (int i = 0; i < rank; ++i) {
     key.w[2 + i] = dims[i];
     key.w[7 + i] = (i + 1 < rank) ? strides_bytes[i] : 0;
@@ -103,8 +107,9 @@ int make_tensor_map(CUtensorMap* out, const void* base, TmaDtype dtype, int rank
     MB_REQUIRE((strides_bytes[i] & 15) == 0,
                "make_tensor_map: stride[%d]=%llu bytes is not a multiple of 16", i,
                (unsigned long long)strides_bytes[i]);
-  MB_REQUIRE(box[0] * esize <= 128, "make_tensor_map: inner box %u elements exceeds 128 bytes",
-             box[0]);
+  MB_REQUIRE(box[0] * esize <= (size_t)swizzle_bytes,
+             "make_tensor_map: inner box %u elements exceeds the %d-byte swizzle span", box[0],
+             swizzle_bytes);
   cuuint64_t gdims[5];
   cuuint64_t gstr[5];
   cuuint32_t gbox[5];
@@ -120,7 +125,8 @@ int make_tensor_map(CUtensorMap* out, const void* base, TmaDtype dtype, int rank
                   dtype == kTmaBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                   static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims, gstr, gbox, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MB_REQUIRE(r == CUDA_SUCCESS,
              "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu box %u,%u)",

@@ -34,7 +34,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int,
          gelu: bool = False, aux_out: torch.Tensor | None = None,
          dgelu_aux: torch.Tensor | None = None,
          atomic: bool = False, k_splits: int = 1, block_n: int = 0,
-         img_hw: tuple[int, int] | None = None) -> torch.Tensor:
+         img_hw: tuple[int, int] | None = None,
+         out_row_map: tuple[int, int, int] | None = None) -> torch.Tensor:
     """out[m, n] = epilogue(A * B^T); see ``mb_gemm`` in include/mirage_b200.h for the contract.
 
     ``a`` / ``b`` are 2-D (or, for MB_A_PATCH32, the [B,1,H,W] fp32 image batch) with unit stride in
@@ -84,5 +85,122 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int,
     args.epilogue = epi
     args.k_splits = k_splits
     args.block_n = block_n
+    if out_row_map is not None:
+        args.out_row_period, args.out_row_stride, args.out_row_offset = out_row_map
     L.check(L.lib().mb_gemm(C.byref(args), _stream()), "mb_gemm")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, heads: int,
+              nq: int, nk: int, head_dim: int, scale: float,
+              out: torch.Tensor | None = None, lse: torch.Tensor | None = None) -> torch.Tensor:
+    """softmax(q k^T * scale) v.  q/k/v are 2-D bf16 views [B*n, ld] (possibly column slices of one
+    fused qkv buffer); returns bf16 [B*nq, heads*head_dim] in token-major / head-minor layout."""
+    _req_cuda(q, k, v, out, lse)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1
+    if out is None:
+        out = torch.empty((batch * nq, heads * head_dim), dtype=torch.bfloat16, device=q.device)
+    a = L.AttnArgs()
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.lse = _ptr(lse)
+    a.batch, a.heads, a.nq, a.nk = batch, heads, nq, nk
+    a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
+    a.head_dim = head_dim
+    a.scale = scale
+    L.check(L.lib().mb_attn_fwd(C.byref(a), _stream()), "mb_attn_fwd")
+    return out
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6, *,
+              out_dtype: torch.dtype = torch.bfloat16, save_stats: bool = False):
+    """Row LayerNorm of an fp32 [rows, dim] tensor.  Returns y (and mean, rstd when save_stats)."""
+    _req_cuda(x, weight, bias)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, dim = x.shape
+    y = torch.empty((rows, dim), dtype=out_dtype, device=x.device)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    L.check(L.lib().mb_layernorm_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(),
+                                     L.MB_BF16 if out_dtype == torch.bfloat16 else L.MB_F32,
+                                     _ptr(mean), _ptr(rstd), rows, dim, x.stride(0), y.stride(0),
+                                     eps, _stream()), "mb_layernorm_fwd")
+    return (y, mean, rstd) if save_stats else y
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, mean: torch.Tensor,
+                  rstd: torch.Tensor, dres: torch.Tensor | None = None):
+    """Returns (dx f32, dweight f32, dbias f32); dx includes dres when given."""
+    _req_cuda(dy, x, weight, mean, rstd, dres)
+    rows, dim = x.shape
+    dx = torch.empty((rows, dim), dtype=torch.float32, device=x.device)
+    dw = torch.empty(dim, dtype=torch.float32, device=x.device)
+    db = torch.empty(dim, dtype=torch.float32, device=x.device)
+    ws = torch.empty(L.lib().mb_layernorm_bwd_workspace(rows, dim), dtype=torch.uint8, device=x.device)
+    L.check(L.lib().mb_layernorm_bwd(dy.data_ptr(), L.MB_BF16 if dy.dtype == torch.bfloat16 else L.MB_F32,
+                                     x.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                     _ptr(dres), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), 0,
+                                     ws.data_ptr(), rows, dim, x.stride(0), dy.stride(0), dx.stride(0),
+                                     _stream()), "mb_layernorm_bwd")
+    return dx, dw, db
+
+
+def colsum(a: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of a 2-D bf16/f32 matrix (bias gradient)."""
+    _req_cuda(a)
+    rows, cols = a.shape
+    out = torch.empty(cols, dtype=torch.float32, device=a.device)
+    ws = torch.empty(L.lib().mb_colsum_workspace(rows, cols), dtype=torch.uint8, device=a.device)
+    L.check(L.lib().mb_colsum(a.data_ptr(), L.MB_BF16 if a.dtype == torch.bfloat16 else L.MB_F32,
+                              out.data_ptr(), 0, ws.data_ptr(), rows, cols, a.stride(0), _stream()),
+            "mb_colsum")
+    return out
+
+
+def token_gather(src: torch.Tensor, ids_keep: torch.Tensor, global_tokens: torch.Tensor) -> torch.Tensor:
+    """[B, n_src, D] fp32, ids [B, n_keep] int64, global [n_glob, D] -> [B, n_keep + n_glob, D]."""
+    _req_cuda(src, ids_keep, global_tokens)
+    B, n_src, D = src.shape
+    n_keep = ids_keep.shape[1]
+    n_glob = global_tokens.shape[0]
+    assert src.is_contiguous() and ids_keep.is_contiguous() and global_tokens.is_contiguous()
+    assert src.dtype == torch.float32 and ids_keep.dtype == torch.int64
+    out = torch.empty((B, n_keep + n_glob, D), dtype=torch.float32, device=src.device)
+    L.check(L.lib().mb_token_gather_fwd(src.data_ptr(), ids_keep.data_ptr(), global_tokens.data_ptr(),
+                                        out.data_ptr(), B, n_src, n_keep, n_glob, D, _stream()),
+            "mb_token_gather_fwd")
+    return out
+
+
+def token_gather_bwd(dout: torch.Tensor, ids_keep: torch.Tensor, n_src: int, n_glob: int):
+    _req_cuda(dout, ids_keep)
+    B, n_out, D = dout.shape
+    n_keep = n_out - n_glob
+    assert dout.is_contiguous() and dout.dtype == torch.float32
+    dsrc = torch.empty((B, n_src, D), dtype=torch.float32, device=dout.device)
+    dglob = torch.empty((n_glob, D), dtype=torch.float32, device=dout.device)
+    L.check(L.lib().mb_token_gather_bwd(dout.data_ptr(), ids_keep.data_ptr(), dsrc.data_ptr(),
+                                        dglob.data_ptr(), B, n_src, n_keep, n_glob, D, _stream()),
+            "mb_token_gather_bwd")
+    return dsrc, dglob
+
+
+def fill_global_rows(global_tokens: torch.Tensor, out: torch.Tensor, row_offset: int):
+    """out[:, row_offset:row_offset+n_glob, :] = global_tokens (out is [B, rows_total, D] fp32)."""
+    _req_cuda(global_tokens, out)
+    B, rows_total, D = out.shape
+    L.check(L.lib().mb_fill_global_rows(global_tokens.data_ptr(), out.data_ptr(), B, rows_total,
+                                        row_offset, global_tokens.shape[0], D, _stream()),
+            "mb_fill_global_rows")
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _req_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().mb_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()),
+            "mb_cast_f32_to_bf16")
     return out
