@@ -55,7 +55,7 @@ def attn_case(B, H, nq, nk, hd, self_attn=True):
 def group_attn64():
     ok = True
     ok &= attn_case(1, 1, 128, 128, 64)
-    ok &= attn_case(1, 1, 128, 256, 64)
+    ok &= attn_case(1, 1, 128, 256, 64, self_attn=False)
     ok &= attn_case(1, 2, 256, 256, 64)
     ok &= attn_case(2, 3, 99, 99, 64)
     ok &= attn_case(2, 12, 513, 513, 64)
