@@ -1,0 +1,396 @@
+"""Autograd-aware building blocks of the MIRAGE hot path, composed from the raw kernels in ops.py.
+
+Data conventions (B200-first, not the reference's):
+  * residual streams are fp32 2-D tensors [B*N, D] (tokens flattened) -- the LayerNorm kernel reads
+    them, the GEMM residual epilogue writes them;
+  * everything that feeds a tensor-core GEMM or the attention kernel is bf16;
+  * parameters stay fp32 ``nn.Parameter``s with the reference's names and shapes; a bf16 shadow of
+    each weight matrix is cached and refreshed when the parameter's version counter moves.
+
+Every ``torch.autograd.Function`` here has a hand-written backward that calls the same C ABI
+(dgrad / wgrad GEMMs, LayerNorm backward, attention backward, ...).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+from . import ops
+
+# ---------------------------------------------------------------------------------------------
+# bf16 weight shadows
+# ---------------------------------------------------------------------------------------------
+_shadow: dict[int, tuple[int, int, torch.Tensor]] = {}
+
+
+def bf16_weight(p: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of an fp32 weight, cached until the parameter is modified in place or replaced."""
+    if p.dtype == torch.bfloat16:
+        return p
+    key = id(p)
+    ver = p._version
+    ent = _shadow.get(key)
+    if ent is not None and ent[0] == ver and ent[1] == p.data_ptr():
+        return ent[2]
+    w = ops.cast_bf16(p.detach().contiguous())
+    _shadow[key] = (ver, p.data_ptr(), w)
+    return w
+
+
+def clear_weight_cache():
+    _shadow.clear()
+
+
+def grad_needed(*tensors) -> bool:
+    """True when autograd is recording and some input wants a gradient.  Evaluated OUTSIDE
+    Function.forward (inside it grad mode is always off), and passed in as the ``save`` flag."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _as_bf16(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype == torch.bfloat16:
+        return t if t.stride(-1) == 1 else t.contiguous()
+    return ops.cast_bf16(t.contiguous())
+
+
+def _wgrad_splits(n_out: int, k_in: int, tokens: int) -> int:
+    tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
+    sms = 148
+    kblocks = (tokens + 63) // 64
+    s = max(1, min(sms // max(tiles, 1), kblocks // 4))
+    return max(1, s)
+
+
+def wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW[n_out, k_in] = dy[T, n_out]^T x[T, k_in] in fp32 (split-K over tokens with atomics)."""
+    T, n_out = dy.shape
+    k_in = x.shape[1]
+    splits = _wgrad_splits(n_out, k_in, T)
+    if splits > 1:
+        out = torch.zeros((n_out, k_in), dtype=torch.float32, device=dy.device)
+    else:
+        out = torch.empty((n_out, k_in), dtype=torch.float32, device=dy.device)
+    ops.gemm(dy, x, m=n_out, n=k_in, k=T, a_layout=L.MB_MAJOR_MN, b_layout=L.MB_MAJOR_MN, out=out,
+             k_splits=splits, atomic=splits > 1)
+    return out
+
+
+def dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, *, out_dtype=torch.bfloat16, dgelu_aux=None) -> torch.Tensor:
+    """dx[T, k_in] = dy[T, n_out] W[n_out, k_in]  (W consumed MN-major: no transposed copy)."""
+    T, n_out = dy.shape
+    k_in = w_bf16.shape[1]
+    return ops.gemm(dy, w_bf16, m=T, n=k_in, k=n_out, b_layout=L.MB_MAJOR_MN, out_dtype=out_dtype,
+                    dgelu_aux=dgelu_aux)
+
+
+# ---------------------------------------------------------------------------------------------
+# Linear
+# ---------------------------------------------------------------------------------------------
+class _Linear(Function):
+    """y = x W^T + b (+ residual), x bf16 [T, K]; y bf16 or fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, out_f32, save):
+        wb = bf16_weight(weight)
+        T, K = x.shape
+        N = weight.shape[0]
+        y = ops.gemm(x, wb, m=T, n=N, k=K, bias=bias, residual=residual,
+                     out_dtype=torch.float32 if (out_f32 or residual is not None) else torch.bfloat16)
+        if save:
+            ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dyb = _as_bf16(dy)
+        dx = dgrad(dyb, bf16_weight(weight)) if ctx.needs_input_grad[0] else None
+        dw = wgrad(dyb, x) if ctx.needs_input_grad[1] else None
+        db = ops.colsum(dyb) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        return dx, dw, db, dres, None, None
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
+    return _Linear.apply(x, weight, bias, residual, out_f32, grad_needed(x, weight, bias, residual))
+
+
+# ---------------------------------------------------------------------------------------------
+# LayerNorm
+# ---------------------------------------------------------------------------------------------
+class _LayerNorm(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_f32, save):
+        if save:
+            y, mean, rstd = ops.layernorm(x, weight, bias, eps, save_stats=True,
+                                          out_dtype=torch.float32 if out_f32 else torch.bfloat16)
+            ctx.save_for_backward(x, weight, mean, rstd)
+        else:
+            y = ops.layernorm(x, weight, bias, eps, out_dtype=torch.float32 if out_f32 else torch.bfloat16)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dx, dw, db = ops.layernorm_bwd(dy.contiguous(), x, weight, mean, rstd)
+        return dx, dw, db, None, None, None
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6,
+               out_f32: bool = False) -> torch.Tensor:
+    """x fp32 [T, D] -> bf16 (GEMM operand) or fp32."""
+    return _LayerNorm.apply(x, weight, bias, eps, out_f32, grad_needed(x, weight, bias))
+
+
+# ---------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------
+class _SelfAttention(Function):
+    """qkv bf16 [B*N, 3D] (fused qkv Linear output) -> o bf16 [B*N, D]."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, N, heads, need):
+        D = qkv.shape[1] // 3
+        hd = D // heads
+        lse = torch.empty((B, heads, N), dtype=torch.float32, device=qkv.device) if need else None
+        o = ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], batch=B, heads=heads, nq=N, nk=N,
+                          head_dim=hd, scale=hd ** -0.5, lse=lse)
+        if need:
+            ctx.save_for_backward(qkv, o, lse)
+            ctx.dims = (B, N, heads, hd)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        B, N, heads, hd = ctx.dims
+        D = heads * hd
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, _as_bf16(do), lse,
+                          dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                          batch=B, heads=heads, nq=N, nk=N, head_dim=hd, scale=hd ** -0.5)
+        return dqkv, None, None, None, None
+
+
+class _CrossAttention(Function):
+    """q bf16 [B*Nq, D], kv bf16 [B*Nk, 2D] -> o bf16 [B*Nq, D]."""
+
+    @staticmethod
+    def forward(ctx, q, kv, B, Nq, Nk, heads, need):
+        D = q.shape[1]
+        hd = D // heads
+        lse = torch.empty((B, heads, Nq), dtype=torch.float32, device=q.device) if need else None
+        o = ops.attention(q, kv[:, :D], kv[:, D:], batch=B, heads=heads, nq=Nq, nk=Nk, head_dim=hd,
+                          scale=hd ** -0.5, lse=lse)
+        if need:
+            ctx.save_for_backward(q, kv, o, lse)
+            ctx.dims = (B, Nq, Nk, heads, hd)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, kv, o, lse = ctx.saved_tensors
+        B, Nq, Nk, heads, hd = ctx.dims
+        D = heads * hd
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        ops.attention_bwd(q, kv[:, :D], kv[:, D:], o, _as_bf16(do), lse, dq, dkv[:, :D], dkv[:, D:],
+                          batch=B, heads=heads, nq=Nq, nk=Nk, head_dim=hd, scale=hd ** -0.5)
+        return dq, dkv, None, None, None, None, None
+
+
+def self_attention(qkv, B, N, heads):
+    return _SelfAttention.apply(qkv, B, N, heads, grad_needed(qkv))
+
+
+def cross_attention(q, kv, B, Nq, Nk, heads):
+    return _CrossAttention.apply(q, kv, B, Nq, Nk, heads, grad_needed(q, kv))
+
+
+# ---------------------------------------------------------------------------------------------
+# MLP:  y = (residual +) fc2(gelu(fc1(x)))
+# ---------------------------------------------------------------------------------------------
+class _Mlp(Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual, need):
+        T, D = x.shape
+        Hd = w1.shape[0]
+        pre = torch.empty((T, Hd), dtype=torch.bfloat16, device=x.device) if need else None
+        g = ops.gemm(x, bf16_weight(w1), m=T, n=Hd, k=D, bias=b1, gelu=True, aux_out=pre)
+        y = ops.gemm(g, bf16_weight(w2), m=T, n=w2.shape[0], k=Hd, bias=b2, residual=residual,
+                     out_dtype=torch.float32 if residual is not None else torch.bfloat16)
+        if need:
+            ctx.save_for_backward(x, w1, w2, pre, g)
+            ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, pre, g = ctx.saved_tensors
+        dyb = _as_bf16(dy)
+        dw2 = wgrad(dyb, g)
+        db2 = ops.colsum(dyb)
+        dpre = dgrad(dyb, bf16_weight(w2), dgelu_aux=pre)      # (dy W2) * gelu'(pre), bf16 [T, Hd]
+        dw1 = wgrad(dpre, x)
+        db1 = ops.colsum(dpre)
+        dx = dgrad(dpre, bf16_weight(w1)) if ctx.needs_input_grad[0] else None
+        dres = dy if ctx.has_res else None
+        return dx, dw1, db1, dw2, db2, dres, None
+
+
+def mlp(x, w1, b1, w2, b2, residual=None):
+    return _Mlp.apply(x, w1, b1, w2, b2, residual, grad_needed(x, w1, b1, w2, b2, residual))
+
+
+# ---------------------------------------------------------------------------------------------
+# fused transformer Block (the hot loop): x fp32 [B*N, D] -> fp32 [B*N, D]
+#   x1 = x  + proj(attn(qkv(LN1(x))));   x2 = x1 + fc2(gelu(fc1(LN2(x1))))
+# mirage/utils.py:259-262.  One autograd node per block: the backward fuses the residual-gradient
+# adds into the LayerNorm-backward kernel and never materialises fp32 copies of bf16 gradients.
+# ---------------------------------------------------------------------------------------------
+class _Block(Function):
+    @staticmethod
+    def forward(ctx, x, B, N, heads, eps, need, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b,
+                fc1_w, fc1_b, fc2_w, fc2_b):
+        T, D = x.shape
+        hd = D // heads
+        params = (n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
+        if need:
+            h1, mean1, rstd1 = ops.layernorm(x, n1w, n1b, eps, save_stats=True)
+        else:
+            h1 = ops.layernorm(x, n1w, n1b, eps)
+        qkv = ops.gemm(h1, bf16_weight(qkv_w), m=T, n=3 * D, k=D, bias=qkv_b)
+        lse = torch.empty((B, heads, N), dtype=torch.float32, device=x.device) if need else None
+        a = ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], batch=B, heads=heads, nq=N, nk=N,
+                          head_dim=hd, scale=hd ** -0.5, lse=lse)
+        x1 = ops.gemm(a, bf16_weight(proj_w), m=T, n=D, k=D, bias=proj_b, residual=x,
+                      out_dtype=torch.float32)
+        if need:
+            h2, mean2, rstd2 = ops.layernorm(x1, n2w, n2b, eps, save_stats=True)
+        else:
+            h2 = ops.layernorm(x1, n2w, n2b, eps)
+        Hd = fc1_w.shape[0]
+        pre = torch.empty((T, Hd), dtype=torch.bfloat16, device=x.device) if need else None
+        g = ops.gemm(h2, bf16_weight(fc1_w), m=T, n=Hd, k=D, bias=fc1_b, gelu=True, aux_out=pre)
+        x2 = ops.gemm(g, bf16_weight(fc2_w), m=T, n=D, k=Hd, bias=fc2_b, residual=x1,
+                      out_dtype=torch.float32)
+        if need:
+            ctx.save_for_backward(x, h1, mean1, rstd1, qkv, a, lse, x1, h2, mean2, rstd2, pre, g, *params)
+            ctx.dims = (B, N, heads, hd)
+        return x2
+
+    @staticmethod
+    def backward(ctx, dx2):
+        (x, h1, mean1, rstd1, qkv, a, lse, x1, h2, mean2, rstd2, pre, g,
+         n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b) = ctx.saved_tensors
+        B, N, heads, hd = ctx.dims
+        D = heads * hd
+        dx2 = dx2.contiguous()
+        dyb = _as_bf16(dx2)
+        # MLP branch
+        d_fc2_w = wgrad(dyb, g)
+        d_fc2_b = ops.colsum(dyb)
+        dpre = dgrad(dyb, bf16_weight(fc2_w), dgelu_aux=pre)
+        d_fc1_w = wgrad(dpre, h2)
+        d_fc1_b = ops.colsum(dpre)
+        dh2 = dgrad(dpre, bf16_weight(fc1_w))
+        dx1, d_n2w, d_n2b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2)
+        # attention branch
+        dx1b = _as_bf16(dx1)
+        d_proj_w = wgrad(dx1b, a)
+        d_proj_b = ops.colsum(dx1b)
+        da = dgrad(dx1b, bf16_weight(proj_w))
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], a, da, lse,
+                          dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                          batch=B, heads=heads, nq=N, nk=N, head_dim=hd, scale=hd ** -0.5)
+        d_qkv_w = wgrad(dqkv, h1)
+        d_qkv_b = ops.colsum(dqkv)
+        dh1 = dgrad(dqkv, bf16_weight(qkv_w))
+        dx, d_n1w, d_n1b = ops.layernorm_bwd(dh1, x, n1w, mean1, rstd1, dres=dx1)
+        return (dx, None, None, None, None, None, d_n1w, d_n1b, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b,
+                d_n2w, d_n2b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b)
+
+
+def transformer_block(x, B, N, heads, eps, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b,
+                      fc1_w, fc1_b, fc2_w, fc2_b):
+    need = grad_needed(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
+    return _Block.apply(x, B, N, heads, eps, need, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b,
+                        fc1_w, fc1_b, fc2_w, fc2_b)
+
+
+# ---------------------------------------------------------------------------------------------
+# visible-token selection
+# ---------------------------------------------------------------------------------------------
+class _TokenGather(Function):
+    @staticmethod
+    def forward(ctx, tokens, ids_keep, global_tokens):
+        ctx.save_for_backward(ids_keep)
+        ctx.n_src = tokens.shape[1]
+        ctx.n_glob = global_tokens.shape[0]
+        return ops.token_gather(tokens.contiguous(), ids_keep.contiguous(), global_tokens.contiguous())
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids_keep,) = ctx.saved_tensors
+        dsrc, dglob = ops.token_gather_bwd(dout.contiguous(), ids_keep.contiguous(), ctx.n_src, ctx.n_glob)
+        return dsrc, None, dglob
+
+
+def token_gather(tokens, ids_keep, global_tokens):
+    """tokens fp32 [B, N_all, D], ids_keep int64 [B, n_keep], global_tokens fp32 [n_glob, D]."""
+    return _TokenGather.apply(tokens, ids_keep, global_tokens)
+
+
+# ---------------------------------------------------------------------------------------------
+# patch embedding (PatchedInputAdapter.proj + pos-emb add)
+# ---------------------------------------------------------------------------------------------
+def patch_tokens_raw(img, weight, bias, pos_rows, out=None, row_map=None):
+    """No-autograd kernel call: img fp32 [B,1,H,W] (32x32 patches) -> fp32 token rows.
+
+    tf32 tensor-core GEMM fed straight from the image by a 5-D TMA box (no im2col); the epilogue adds
+    the conv bias and the positional-embedding row and can write into a slice of a larger
+    [B, N_all(+global), D] token buffer through ``row_map = (period, stride, offset)``.
+    """
+    Bn, _, H, W = img.shape
+    D = weight.shape[0]
+    n_tok = (H // 32) * (W // 32)
+    if out is None:
+        out = torch.empty((Bn * n_tok, D), dtype=torch.float32, device=img.device)
+    ops.gemm(img.contiguous(), weight.detach().reshape(D, 1024), m=Bn * n_tok, n=D, k=1024,
+             a_layout=L.MB_A_PATCH32, img_hw=(H, W), bias=bias.detach(), residual=pos_rows,
+             res_period=n_tok, out=out, out_row_map=row_map)
+    return out
+
+
+def patch_wgrad(img, dtok_bf16):
+    """dW[D, 1024] of the 32x32 patch embedding; the bf16 im2col exists only here, never in forward."""
+    Bn, _, H, W = img.shape
+    gh, gw = H // 32, W // 32
+    patches = img.reshape(Bn, gh, 32, gw, 32).permute(0, 1, 3, 2, 4).reshape(Bn * gh * gw, 1024)
+    return wgrad(dtok_bf16, _as_bf16(patches.contiguous()))
+
+
+class _PatchEmbed32(Function):
+    @staticmethod
+    def forward(ctx, img, weight, bias, pos_rows):
+        ctx.save_for_backward(img, weight)
+        return patch_tokens_raw(img, weight, bias, pos_rows)
+
+    @staticmethod
+    def backward(ctx, dout):
+        img, weight = ctx.saved_tensors
+        dyb = _as_bf16(dout.contiguous())
+        dw = patch_wgrad(img, dyb).reshape(weight.shape)
+        return None, dw, ops.colsum(dyb), None
+
+
+def patch_embed32(img, weight, bias, pos_rows):
+    """Autograd version: returns fresh fp32 [B*n_tok, D]."""
+    return _PatchEmbed32.apply(img, weight, bias, pos_rows)

@@ -1,0 +1,73 @@
+"""Encoder-only MIRAGE wrapper with the API of the reference's ``hf/mirage_hf.py`` (:582-692).
+
+``MIRAGEWrapper(input_size=512, patch_size=32, modalities='bscan-slo', size='base'|'large')``
+needs no checkpoint (random init); ``forward({'bscan': [B,1,H,W], 'slo': [B,1,H,W]})`` returns the
+encoder tokens ``[B, N_all + 1, D]`` (global token last, no final norm).  ``load_state_dict``
+forwards to ``self.model`` (keys without the ``model.`` prefix), as the reference does.
+"""
+from __future__ import annotations
+
+import argparse
+from functools import partial
+from typing import Any, Mapping
+
+import torch
+from torch import nn
+
+from .input_adapters import PatchedInputAdapter
+from .model import MIRAGELight
+from .utils import pair
+
+_SIZES = {'base': dict(dim_tokens=768, depth=12, num_heads=12),
+          'large': dict(dim_tokens=1024, depth=24, num_heads=16)}
+
+
+class MIRAGEWrapper(nn.Module):
+    def __init__(self, input_size=512, patch_size=32, modalities='bscan-slo', size='base'):
+        super().__init__()
+        self.domain_conf = {'bscan': self.default_domain_conf(), 'slo': self.default_domain_conf()}
+        self.size = size
+
+        args = argparse.Namespace()
+        args.num_global_tokens = 1
+        args.drop_path = 0.0
+        args.in_domains = modalities.split('-')
+        input_size, patch_size = pair(input_size), pair(patch_size)
+        assert input_size is not None and patch_size is not None
+        args.patch_size, args.input_size, args.grid_sizes = {}, {}, {}
+        for domain in args.in_domains:
+            args.patch_size[domain] = patch_size
+            args.input_size[domain] = input_size
+            args.grid_sizes[domain] = [input_size[i] // patch_size[i] for i in range(len(input_size))]
+        self.args = args
+        self.model = self.get_model()
+
+    def default_domain_conf(self):
+        return {'channels': 1, 'stride_level': 1,
+                'input_adapter': partial(PatchedInputAdapter, num_channels=1), 'output_adapter': None}
+
+    def get_model(self):
+        if self.size not in _SIZES:
+            raise ValueError('Unknown model size:', self.size)
+        input_adapters = {
+            domain: self.domain_conf[domain]['input_adapter'](
+                stride_level=self.domain_conf[domain]['stride_level'],
+                patch_size_full=tuple(self.args.patch_size[domain]),
+                image_size=self.args.input_size[domain])
+            for domain in self.args.in_domains
+        }
+        return MIRAGELight(args=self.args, input_adapters=input_adapters, output_adapters=None,
+                           num_global_tokens=self.args.num_global_tokens,
+                           drop_path_rate=self.args.drop_path, mlp_ratio=4, qkv_bias=True,
+                           norm_layer=partial(nn.LayerNorm, eps=1e-6), **_SIZES[self.size])
+
+    def forward(self, x: dict):
+        """x: {modality: [B, 1, H, W] in [0, 1]} -> encoder tokens [B, N_all + 1, D]."""
+        return self.model(x)
+
+    def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True, assign: bool = False):
+        return self.model.load_state_dict(state_dict, strict, assign)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
