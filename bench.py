@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the MIRAGE MultiViT hot path on B200 (the driver's contract).
+
+  python bench.py --gpus N --steps K --warmup W [--workload encoder_large|pretrain_large|...]
+  python bench.py --impl reference ...     # the reference's CPU arithmetic (oracle port) on host cores
+
+Default workload (N=1) = BASELINE.json configs[1]: MIRAGE-Large encoder inference, bscan+slo 512x512,
+256 images per GPU per step, bf16 tensor-core math.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# algorithmic FLOPs per sample (forward), SURVEY.md section 8(d) / BASELINE.md section 4
+GFLOP_FWD = {"encoder_base": 97.65, "encoder_large": 336.79, "pretrain_base": 24.07, "pretrain_large": 68.49}
+
+WORKLOADS = {
+    # name: (size, modalities, per-GPU batch, kind)
+    "encoder_large": ("large", ["bscan", "slo"], 256, "encoder"),
+    "encoder_base": ("base", ["bscan", "slo"], 256, "encoder"),
+    "pretrain_large": ("large", ["bscan", "slo", "bscanlayermap"], 256, "pretrain"),
+    "pretrain_base": ("base", ["bscan", "slo", "bscanlayermap"], 256, "pretrain"),
+}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                    "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle (CPU) legs
+# ---------------------------------------------------------------------------------------------
+def cpu_oracle_throughput(workload: str, budget_s: float = 20.0, batch: int = 2, seed: int = 0):
+    """Times the reference's arithmetic (oracle port, fp32, all host threads) on a bounded sample of the
+    same workload.  Returns (samples/s, cores, description)."""
+    from oracle import mirage_oracle as O
+    sys.path.insert(0, str(ROOT / "tests"))
+    from helpers import synth_images, synth_state_dict
+    size, mods, _, kind = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    depth, heads = (12, 12) if size == "base" else (24, 16)
+    if kind == "encoder":
+        from mirage_b200.mirage_hf import MIRAGEWrapper
+        with torch.device("cpu"):
+            m = MIRAGEWrapper(size=size, modalities="-".join(mods))
+        sd = m.model.state_dict()
+        sd.update(synth_state_dict({k: v.shape for k, v in sd.items()}, seed))
+        x = synth_images(batch, mods, seed=1234)
+
+        def run():
+            with torch.no_grad():
+                return O.light_forward(x, sd, depth, heads)
+    else:
+        from bench_support import build_pretrain_oracle
+        run = build_pretrain_oracle(size, mods, batch, seed)
+    run()  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        run()
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 8:
+            break
+    return batch * n / el, cores, f"{n} x batch {batch} of {workload}, fp32 oracle, {cores} threads"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warm = max(1, args.steps), args.warmup
+    budget = min(25.0, 120.0 / max(1, steps))
+    vals = []
+    desc = ""
+    cores = os.cpu_count() or 1
+    for i in range(min(warm, 1) + steps):
+        v, cores, desc = cpu_oracle_throughput(args.workload, budget_s=budget / 2, batch=2)
+        if i >= min(warm, 1):
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    size, mods, per_gpu, kind = WORKLOADS[args.workload]
+    unit = "images/s" if kind == "encoder" else "samples/s"
+    line = {
+        "impl": "reference", "metric": f"{args.workload} {unit}", "value": value, "unit": unit,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * 2 / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "modalities": mods, "per_step_sample": desc},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class KernelTimer:
+    """Per-launch CUDA-event timing on the launching stream, grouped by kernel name."""
+
+    def __init__(self):
+        self.records = []
+
+    def __call__(self, name, work, unit):
+        timer = self
+
+        class _Ctx:
+            def __enter__(self_):
+                self_.e0 = torch.cuda.Event(enable_timing=True)
+                self_.e1 = torch.cuda.Event(enable_timing=True)
+                self_.e0.record()
+
+            def __exit__(self_, *a):
+                self_.e1.record()
+                timer.records.append((name, work, unit, self_.e0, self_.e1))
+                return False
+        return _Ctx()
+
+    def summary(self):
+        agg = {}
+        for name, work, unit, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            a = agg.setdefault(name, {"ms": 0.0, "work": 0.0, "unit": unit, "launches": 0})
+            a["ms"] += ms
+            a["work"] += work
+            a["launches"] += 1
+        return agg
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    from mirage_b200 import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the MIRAGE hot path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    size, mods, per_gpu, kind = WORKLOADS[args.workload]
+    if args.batch:
+        per_gpu = args.batch
+    sys.path.insert(0, str(ROOT / "tests"))
+    from helpers import load_synth, synth_images
+
+    if kind == "encoder":
+        from mirage_b200.mirage_hf import MIRAGEWrapper
+        model = MIRAGEWrapper(size=size, modalities="-".join(mods))
+        load_synth(model.model, seed=0)
+        model = model.to(dev).eval()
+        base = synth_images(8, mods, seed=1234 + rank)
+        host_in = {k: v.repeat(per_gpu // 8 + 1, 1, 1, 1)[:per_gpu].contiguous().pin_memory()
+                   for k, v in base.items()}
+        dev_in = {k: v.to(dev) for k, v in host_in.items()}
+        n_tok = sum((v.shape[-1] // 32) * (v.shape[-2] // 32) for v in dev_in.values()) + 1
+        D = model.model.dim_tokens
+        host_out = torch.empty((per_gpu, n_tok, D), dtype=torch.float32).pin_memory()
+
+        def step():
+            with torch.no_grad():
+                return model(dev_in)
+
+        def step_e2e():
+            with torch.no_grad():
+                xin = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
+                out = model(xin)
+                host_out.copy_(out, non_blocking=True)
+            return out
+        h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+        d2h = host_out.numel() * host_out.element_size()
+        flop_per_sample = GFLOP_FWD[args.workload] * 1e9
+        unit = "images/s"
+    else:
+        from bench_support import build_pretrain_step
+        step, step_e2e, h2d, d2h = build_pretrain_step(size, mods, per_gpu, dev, rank, world)
+        flop_per_sample = 3.0 * GFLOP_FWD[args.workload] * 1e9
+        unit = "samples/s"
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    W, K = max(3, args.warmup), max(1, args.steps)
+    for _ in range(W):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end-to-end through the public API with host buffers (H2D + D2H inside the timed region)
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    e0.record()
+    for _ in range(K):
+        step_e2e()
+    e1.record()
+    sync_all()
+    ms_e2e = e0.elapsed_time(e1)
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = t.tolist()
+
+    # per-kernel roofline pass: one more step with CUDA events around every launch (rank 0)
+    roofline = None
+    kernels = None
+    if rank == 0:
+        kt = KernelTimer()
+        ops.set_recorder(kt)
+        step()
+        torch.cuda.synchronize()
+        ops.set_recorder(None)
+        agg = kt.summary()
+        peaks = measured_peaks()
+        tot = sum(a["ms"] for a in agg.values()) or 1.0
+        kernels = {k: {"ms": round(a["ms"], 3), "share": round(a["ms"] / tot, 3), "launches": a["launches"],
+                       ("tflops" if a["unit"] == "flop" else "gbs"):
+                           round(a["work"] / a["ms"] / (1e9 if a["unit"] == "flop" else 1e6), 1)}
+                   for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+        top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+        name, a = top
+        if a["unit"] == "flop":
+            ach = a["work"] / a["ms"] / 1e9
+            peak = peaks["bf16_tflops_sustained"]
+            roofline = {"kernel": name, "bound": "tensor", "achieved": round(ach, 1), "peak": peak,
+                        "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
+                        "peak_source": peaks["source"] + " (sustained bf16)",
+                        "per_launch": {"flops": a["work"] / a["launches"], "ms": a["ms"] / a["launches"]}}
+        else:
+            ach = a["work"] / a["ms"] / 1e6
+            peak = peaks["hbm_gbs"]
+            roofline = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak,
+                        "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                        "peak_source": peaks["source"],
+                        "per_launch": {"bytes": a["work"] / a["launches"], "ms": a["ms"] / a["launches"]}}
+
+    if rank == 0:
+        total = per_gpu * world * K
+        value = total / (ms_total / 1e3)
+        e2e_v = total / (ms_e2e / 1e3)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, desc = cpu_oracle_throughput(args.workload, budget_s=15.0, batch=2)
+            cpu = {"value": round(v, 3), "unit": unit, "cores": cores, "kind": "port", "sample": desc}
+        peaks = measured_peaks()
+        line = {
+            "metric": f"{args.workload} {unit}", "value": round(value, 2), "unit": unit,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "size": size, "modalities": mods,
+                       "per_gpu_batch": per_gpu, "global_batch": per_gpu * world,
+                       "parallelism": f"dp{world} (batch-sharded, no collective)" if kind == "encoder"
+                       else f"dp{world} (NCCL gradient all-reduce)",
+                       "l2_policy": "inputs_exceed_l2 (activations >> 126 MB per step)"},
+            "model_tflops": round(value * flop_per_sample / 1e12, 1),
+            "model_frac_of_bf16_peak": round(value * flop_per_sample / 1e12 / world / peaks["bf16_tflops"], 4),
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "e2e": {"value": round(e2e_v, 2), "unit": unit, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="encoder_large", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", __file__] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -63,10 +63,13 @@ void mb_clear_tensor_map_cache(void);
  *      r(m) = m, or with out_row_period = P > 0:  r(m) = (m / P) * out_row_stride + m % P +
  *      out_row_offset -- this lets each input adapter write its tokens straight into its slice of
  *      the concatenated [B, N_all (+ global), D] token buffer (the torch.cat of model.py:384/:520).
+ *      With MB_EPI_UNPATCH the store un-patchifies instead (output_adapters.py:291-294):
+ *      row m = (b, nh, nw), column n = (c, py, px) lands at image pixel
+ *      out[b, c, nh*up_ph + py, nw*up_pw + px] of a [B, up_channels, up_gh*up_ph, up_gw*up_pw] tensor.
  */
 enum { MB_BF16 = 0, MB_F32 = 1 };
 enum { MB_MAJOR_K = 0, MB_MAJOR_MN = 1, MB_A_PATCH32 = 2 };
-enum { MB_EPI_GELU = 1, MB_EPI_DGELU = 2, MB_EPI_ATOMIC = 4 };
+enum { MB_EPI_GELU = 1, MB_EPI_DGELU = 2, MB_EPI_ATOMIC = 4, MB_EPI_UNPATCH = 8 };
 
 typedef struct mb_gemm_args {
   const void* a;      /* bf16 (or f32 when in_dtype == MB_F32) */
@@ -88,6 +91,7 @@ typedef struct mb_gemm_args {
   int32_t block_n;    /* 0 = auto, else 64 / 128 / 256 */
   int32_t img_h, img_w; /* MB_A_PATCH32 only */
   int64_t out_row_period, out_row_stride, out_row_offset; /* 0,0,0 = identity row map */
+  int32_t up_channels, up_ph, up_pw, up_gh, up_gw;        /* MB_EPI_UNPATCH only */
 } mb_gemm_args;
 
 int mb_gemm(const mb_gemm_args* args, void* stream);
@@ -119,6 +123,30 @@ typedef struct mb_attn_args {
 } mb_attn_args;
 
 int mb_attn_fwd(const mb_attn_args* args, void* stream);
+
+/* Attention backward (autograd of the call sites above).  Inputs: the forward's q/k/v/out/lse and
+ * d_out (bf16, same layout as out).  Outputs dq/dk/dv: bf16, token-major like q/k/v (they may be
+ * column slices of one fused [B*N, 3*D] gradient buffer).  When nk > 128 a workspace of
+ * mb_attn_bwd_workspace() bytes is required (fp32 dQ accumulation across key blocks). */
+typedef struct mb_attn_bwd_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* out;
+  const void* d_out;
+  const float* lse;
+  void* dq;
+  void* dk;
+  void* dv;
+  void* workspace;
+  int64_t batch, heads, nq, nk;
+  int64_t ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+  int32_t head_dim;
+  float scale;
+} mb_attn_bwd_args;
+
+int64_t mb_attn_bwd_workspace(int64_t batch, int64_t heads, int64_t nq, int64_t nk, int32_t head_dim);
+int mb_attn_bwd(const mb_attn_bwd_args* args, void* stream);
 
 /* ---------------------------------------------------------------- row kernels (HBM-bound) -- */
 /* LayerNorm(eps) with affine, fp32 statistics.  nn.LayerNorm at mirage/utils.py:241,250,260-261,
@@ -159,6 +187,61 @@ int mb_token_gather_bwd(const float* dout, const int64_t* ids_keep, float* dsrc,
 int mb_fill_global_rows(const float* global_tokens, float* out, int64_t batch, int64_t rows_total,
                         int64_t row_offset, int64_t n_global, int64_t dim, void* stream);
 int mb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- adapters ----------------- */
+/* SemSegInputAdapter (mirage/input_adapters.py:226-229): class-embedding lookup fused with patch
+ * extraction.  out[m, c*P*Q + ph*Q + pw] = class_emb[labels[b, nh*P+ph, nw*Q+pw], c] (bf16), the A
+ * operand of the patch-projection GEMM, m = (b, nh, nw), K order (c, ph, pw) as Conv2d's weight. */
+int mb_semseg_patches(const int64_t* labels, const void* class_emb_bf16, void* out, int64_t batch,
+                      int64_t height, int64_t width, int32_t patch_h, int32_t patch_w,
+                      int32_t n_classes, int32_t emb_dim, void* stream);
+/* d_class_emb[cls, c] = sum of d_patches over every pixel whose label is cls (f32 [n_classes, emb_dim]). */
+int mb_class_emb_grad(const int64_t* labels, const void* d_patches_bf16, float* d_class_emb,
+                      int64_t batch, int64_t height, int64_t width, int32_t patch_h, int32_t patch_w,
+                      int32_t n_classes, int32_t emb_dim, void* stream);
+
+/* SpatialOutputAdapter.get_queries_and_context (mirage/output_adapters.py:188-246), use_task_queries:
+ *   queries[b, t] = (r < n_vis ? ctx[b, r] : mask_token) + emb[q_start + t],  r = ids_restore[b, q_start + t]
+ *   context[b, j] = (r2 < n_vis ? ctx[b, r2] : mask_token) + emb[ids_keep[b, j]],  r2 = ids_restore[b, ids_keep[b, j]]
+ *   context[b, n_vis + g] = ctx[b, n_vis + g]            (global tokens get no embedding, :240-242)
+ * ctx f32 [B, n_vis + n_global, dim] (proj_context output), emb f32 [n_all, dim] = task_emb + pos_emb
+ * (added in that order, :180).  Bit-exact with the reference's cat/gather/add sequence in fp32. */
+int mb_dec_assemble_fwd(const float* ctx, const float* mask_token, const float* emb,
+                        const int64_t* ids_keep, const int64_t* ids_restore, float* queries,
+                        float* context, int64_t batch, int64_t n_vis, int64_t n_global, int64_t n_all,
+                        int64_t q_start, int64_t n_q, int64_t dim, void* stream);
+/* Backward; ids_restore must be the inverse permutation of the shuffle behind ids_keep (it always is
+ * on the path: model.py:225-227, :380-382).  workspace: n_q * dim * 4 bytes. */
+int mb_dec_assemble_bwd(const float* d_queries, const float* d_context, const int64_t* ids_keep,
+                        const int64_t* ids_restore, float* d_ctx, float* d_emb, float* d_mask_token,
+                        void* workspace, int64_t batch, int64_t n_vis, int64_t n_global,
+                        int64_t n_all, int64_t q_start, int64_t n_q, int64_t dim, void* stream);
+
+/* image [B, C, gh*ph, gw*pw] f32 -> tokens [B*gh*gw, C*ph*pw] bf16: backward of the un-patchify
+ * (output_adapters.py:291-294), producing the dgrad/wgrad operand of out_proj. */
+int mb_patchify_cast(const float* img, void* out_bf16, int64_t batch, int32_t channels, int32_t ph,
+                     int32_t pw, int32_t gh, int32_t gw, void* stream);
+
+/* ---------------------------------------------------------------- masked criteria ---------- */
+/* MaskedMSELoss (mirage/criterion.py:87-117, norm_pix=False) and MaskedCrossEntropyLoss (:31-51).
+ * pred/target f32 [B,C,H,W] (CE: logits f32 [B,C,H,W], target i64 [B,H,W]); mask i64 [B, (H/scale)*(W/scale)]
+ * with 1 = masked-out token (contributes to the loss), or NULL (plain mean).  loss: f32 scalar;
+ * coef: f32 [B] saved for the backward.  An all-zero mask yields 0.0 (the reference returns an int64
+ * tensor(0) after a host sync; here nothing is read back).  workspace: mb_masked_loss_workspace() bytes. */
+int64_t mb_masked_loss_workspace(int64_t batch, int64_t height, int64_t width);
+int mb_masked_mse_fwd(const float* pred, const float* target, const int64_t* mask, float* loss,
+                      float* coef, void* workspace, int64_t batch, int64_t channels, int64_t height,
+                      int64_t width, int32_t scale, void* stream);
+int mb_masked_mse_bwd(const float* pred, const float* target, const int64_t* mask, const float* coef,
+                      const float* grad_out, float* dpred, int64_t batch, int64_t channels,
+                      int64_t height, int64_t width, int32_t scale, void* stream);
+int mb_masked_ce_fwd(const float* logits, const int64_t* target, const int64_t* mask, float* loss,
+                     float* coef, void* workspace, int64_t batch, int64_t channels, int64_t height,
+                     int64_t width, int32_t scale, float label_smoothing, void* stream);
+int mb_masked_ce_bwd(const float* logits, const int64_t* target, const int64_t* mask,
+                     const float* coef, const float* grad_out, float* dlogits, int64_t batch,
+                     int64_t channels, int64_t height, int64_t width, int32_t scale,
+                     float label_smoothing, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ LIB_PATH = PKG_DIR / "libmirage_b200.so"
 # enums mirrored from include/mirage_b200.h
 MB_BF16, MB_F32 = 0, 1
 MB_MAJOR_K, MB_MAJOR_MN, MB_A_PATCH32 = 0, 1, 2
-MB_EPI_GELU, MB_EPI_DGELU, MB_EPI_ATOMIC = 1, 2, 4
+MB_EPI_GELU, MB_EPI_DGELU, MB_EPI_ATOMIC, MB_EPI_UNPATCH = 1, 2, 4, 8
 
 
 class MirageB200Error(RuntimeError):
@@ -35,6 +35,8 @@ class GemmArgs(C.Structure):
         ("epilogue", C.c_int32), ("k_splits", C.c_int32), ("block_n", C.c_int32),
         ("img_h", C.c_int32), ("img_w", C.c_int32),
         ("out_row_period", C.c_int64), ("out_row_stride", C.c_int64), ("out_row_offset", C.c_int64),
+        ("up_channels", C.c_int32), ("up_ph", C.c_int32), ("up_pw", C.c_int32),
+        ("up_gh", C.c_int32), ("up_gw", C.c_int32),
     ]
 
 
@@ -44,6 +46,18 @@ class AttnArgs(C.Structure):
         ("lse", C.c_void_p),
         ("batch", C.c_int64), ("heads", C.c_int64), ("nq", C.c_int64), ("nk", C.c_int64),
         ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
+        ("head_dim", C.c_int32), ("scale", C.c_float),
+    ]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("d_out", C.c_void_p), ("lse", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("workspace", C.c_void_p),
+        ("batch", C.c_int64), ("heads", C.c_int64), ("nq", C.c_int64), ("nk", C.c_int64),
+        ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
+        ("lddo", C.c_int64), ("lddq", C.c_int64), ("lddk", C.c_int64), ("lddv", C.c_int64),
         ("head_dim", C.c_int32), ("scale", C.c_float),
     ]
 
@@ -62,6 +76,12 @@ def _declare(lib):
     lib.mb_gemm.argtypes = [C.POINTER(GemmArgs), vp]
     lib.mb_attn_fwd.restype = C.c_int
     lib.mb_attn_fwd.argtypes = [C.POINTER(AttnArgs), vp]
+    lib.mb_attn_bwd.restype = C.c_int
+    lib.mb_attn_bwd.argtypes = [C.POINTER(AttnBwdArgs), vp]
+    lib.mb_attn_bwd_workspace.restype = C.c_int64
+    lib.mb_attn_bwd_workspace.argtypes = [i64, i64, i64, i64, i32]
+    lib.mb_masked_loss_workspace.restype = C.c_int64
+    lib.mb_masked_loss_workspace.argtypes = [i64, i64, i64]
     for name in ("mb_layernorm_bwd_workspace", "mb_colsum_workspace"):
         getattr(lib, name).restype = C.c_int64
         getattr(lib, name).argtypes = [i64, i64]
@@ -85,11 +105,22 @@ SIGNATURES: dict[str, list] = {
     "mb_token_gather_bwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
     "mb_fill_global_rows": [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
     "mb_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
+    "mb_semseg_patches": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
+    "mb_class_emb_grad": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
+    "mb_dec_assemble_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp],
+    "mb_dec_assemble_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
+                            _i64, _vp],
+    "mb_patchify_cast": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
+    "mb_masked_mse_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
+    "mb_masked_mse_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
+    "mb_masked_ce_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp],
+    "mb_masked_ce_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp],
 }
 
 # every symbol include/mirage_b200.h declares
 EXPORTED = ["mb_last_error", "mb_version", "mb_sm_count", "mb_clear_tensor_map_cache", "mb_gemm",
-            "mb_attn_fwd", "mb_layernorm_bwd_workspace", "mb_colsum_workspace"]
+            "mb_attn_fwd", "mb_attn_bwd", "mb_attn_bwd_workspace", "mb_layernorm_bwd_workspace",
+            "mb_colsum_workspace", "mb_masked_loss_workspace"]
 
 
 def lib():

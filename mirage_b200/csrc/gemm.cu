@@ -38,6 +38,8 @@ struct GemmDev {
   // output row map
   int orow_period;
   long long orow_stride, orow_offset;
+  // MB_EPI_UNPATCH: token-major [B*gh*gw, C*ph*pw] -> image [B, C, gh*ph, gw*pw]
+  int up_c, up_ph, up_pw, up_gh, up_gw;
 };
 
 constexpr int kGemmThreads = 384;
@@ -213,6 +215,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               ? (long long)(row / p.orow_period) * p.orow_stride + row % p.orow_period + p.orow_offset
               : (long long)row;
 
+      long long up_base = 0;  // offset of pixel (b, c=0, nh*ph, nw*pw)
+      if (p.epilogue & MB_EPI_UNPATCH) {
+        const int per_img = p.up_gh * p.up_gw;
+        const int bi = row / per_img, t = row - bi * per_img;
+        const int nh = t / p.up_gw, nw = t - nh * p.up_gw;
+        const long long W = (long long)p.up_gw * p.up_pw, H = (long long)p.up_gh * p.up_ph;
+        up_base = ((long long)bi * p.up_c * H + (long long)nh * p.up_ph) * W + (long long)nw * p.up_pw;
+      }
       mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -267,12 +277,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
               f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
             }
+            long long oidx = orow * p.ldc + col;
+            if (p.epilogue & MB_EPI_UNPATCH) {
+              const int pp = p.up_ph * p.up_pw;
+              const int ch = col / pp, rr = col - ch * pp;
+              const int py = rr / p.up_pw, px = rr - py * p.up_pw;
+              const long long W = (long long)p.up_gw * p.up_pw, H = (long long)p.up_gh * p.up_ph;
+              oidx = up_base + ((long long)ch * H + py) * W + px;
+            }
             if (p.epilogue & MB_EPI_ATOMIC) {
-              float* o = reinterpret_cast<float*>(p.out) + orow * p.ldc + col;
+              float* o = reinterpret_cast<float*>(p.out) + oidx;
 #pragma unroll
               for (int i = 0; i < 8; ++i) atomicAdd(o + i, f[i]);
             } else if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + orow * p.ldc + col;
+              float* o = reinterpret_cast<float*>(p.out) + oidx;
               *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
               *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
             } else {
@@ -282,7 +300,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               pk.z = pack_bf16x2(f[4], f[5]);
               pk.w = pack_bf16x2(f[6], f[7]);
               __nv_bfloat16* o =
-                  reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + col;
+                  reinterpret_cast<__nv_bfloat16*>(p.out) + oidx;
               *reinterpret_cast<uint4*>(o) = pk;
             }
           }
@@ -354,7 +372,8 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
              (long long)a->m, (long long)a->n, (long long)a->k);
   MB_REQUIRE(a->m < (1ll << 31) && a->n < (1ll << 31) && a->k < (1ll << 31), "mb_gemm: too large");
   MB_REQUIRE(a->n % 8 == 0, "mb_gemm: N=%lld must be a multiple of 8", (long long)a->n);
-  MB_REQUIRE(a->ldc % 8 == 0, "mb_gemm: ldc=%lld must be a multiple of 8", (long long)a->ldc);
+  MB_REQUIRE(a->ldc % 8 == 0 || (a->epilogue & MB_EPI_UNPATCH),
+             "mb_gemm: ldc=%lld must be a multiple of 8", (long long)a->ldc);
   MB_REQUIRE(a->a && a->b && a->out, "mb_gemm: null operand pointer");
   MB_REQUIRE(a->k_splits >= 1, "mb_gemm: k_splits must be >= 1");
   MB_REQUIRE(a->k_splits == 1 || (a->epilogue & MB_EPI_ATOMIC),
@@ -396,6 +415,21 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
   p.total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
   p.rows_per_img = 0;
   p.grid_w = 0;
+  p.up_c = a->up_channels;
+  p.up_ph = a->up_ph;
+  p.up_pw = a->up_pw;
+  p.up_gh = a->up_gh;
+  p.up_gw = a->up_gw;
+  if (a->epilogue & MB_EPI_UNPATCH) {
+    MB_REQUIRE(a->up_channels > 0 && a->up_ph > 0 && a->up_pw > 0 && a->up_gh > 0 && a->up_gw > 0,
+               "mb_gemm: MB_EPI_UNPATCH needs up_* geometry");
+    MB_REQUIRE(a->up_pw % 8 == 0, "mb_gemm: MB_EPI_UNPATCH needs patch width %% 8 == 0");
+    MB_REQUIRE(a->n == (int64_t)a->up_channels * a->up_ph * a->up_pw,
+               "mb_gemm: MB_EPI_UNPATCH needs N = C*ph*pw");
+    MB_REQUIRE(a->m % ((int64_t)a->up_gh * a->up_gw) == 0,
+               "mb_gemm: MB_EPI_UNPATCH needs M multiple of gh*gw");
+    MB_REQUIRE(a->out_row_period == 0, "mb_gemm: MB_EPI_UNPATCH excludes the output row map");
+  }
   p.orow_period = (int)a->out_row_period;
   p.orow_stride = a->out_row_stride;
   p.orow_offset = a->out_row_offset;

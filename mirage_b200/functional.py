@@ -394,3 +394,174 @@ class _PatchEmbed32(Function):
 def patch_embed32(img, weight, bias, pos_rows):
     """Autograd version: returns fresh fp32 [B*n_tok, D]."""
     return _PatchEmbed32.apply(img, weight, bias, pos_rows)
+
+
+# ---------------------------------------------------------------------------------------------
+# SemSegInputAdapter: embedding lookup + patch projection (+ pos-emb) -- input_adapters.py:226-236
+# ---------------------------------------------------------------------------------------------
+class _SemSegEmbed(Function):
+    @staticmethod
+    def forward(ctx, labels, class_emb, weight, bias, pos_rows, ph, pw, save):
+        D = weight.shape[0]
+        a = ops.semseg_patches(labels.contiguous(), bf16_weight(class_emb), ph, pw)   # [M, E*ph*pw] bf16
+        w2d = bf16_weight(weight).reshape(D, -1)
+        n_tok = pos_rows.shape[0]
+        out = ops.gemm(a, w2d, m=a.shape[0], n=D, k=a.shape[1], bias=bias, residual=pos_rows,
+                       res_period=n_tok, out_dtype=torch.float32)
+        if save:
+            ctx.save_for_backward(labels, a, class_emb, weight)
+            ctx.geom = (ph, pw)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        labels, a, class_emb, weight = ctx.saved_tensors
+        ph, pw = ctx.geom
+        D = weight.shape[0]
+        dyb = _as_bf16(dout.contiguous())
+        dw = wgrad(dyb, a).reshape(weight.shape)
+        db = ops.colsum(dyb)
+        d_a = dgrad(dyb, bf16_weight(weight).reshape(D, -1))                     # [M, E*ph*pw] bf16
+        d_emb = ops.class_emb_grad(labels, d_a, class_emb.shape[0], class_emb.shape[1], ph, pw)
+        return None, d_emb, dw, db, None, None, None, None
+
+
+def semseg_embed(labels, class_emb, weight, bias, pos_rows, ph, pw):
+    """labels int64 [B,H,W] -> fp32 [B*n_tok, D]."""
+    return _SemSegEmbed.apply(labels, class_emb, weight, bias, pos_rows, ph, pw,
+                              grad_needed(class_emb, weight, bias))
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32 -> bf16 cast as an autograd node (feeds a GEMM from an fp32 residual stream)
+# ---------------------------------------------------------------------------------------------
+class _ToBf16(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.cast_bf16(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy.float()
+
+
+def to_bf16(x):
+    return x if x.dtype == torch.bfloat16 else _ToBf16.apply(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# decoder queries / context (output_adapters.py:188-246)
+# ---------------------------------------------------------------------------------------------
+class _DecAssemble(Function):
+    @staticmethod
+    def forward(ctx, ctx_tok, mask_token, emb, ids_keep, ids_restore, q_start, n_q, n_glob):
+        q, c = ops.dec_assemble(ctx_tok.contiguous(), mask_token.contiguous(), emb.contiguous(),
+                                ids_keep.contiguous(), ids_restore.contiguous(), q_start, n_q, n_glob)
+        ctx.save_for_backward(ids_keep, ids_restore)
+        ctx.geom = (q_start, n_glob)
+        return q, c
+
+    @staticmethod
+    def backward(ctx, dq, dc):
+        ids_keep, ids_restore = ctx.saved_tensors
+        q_start, n_glob = ctx.geom
+        dctx, demb, dmask = ops.dec_assemble_bwd(dq.contiguous(), dc.contiguous(), ids_keep.contiguous(),
+                                                 ids_restore.contiguous(), q_start, n_glob)
+        return dctx, dmask, demb, None, None, None, None, None
+
+
+def dec_assemble(ctx_tok, mask_token, emb, ids_keep, ids_restore, q_start, n_q, n_glob):
+    """ctx_tok fp32 [B, n_vis+n_glob, Dd]; mask_token [Dd]; emb [N_all, Dd] -> (queries, context)."""
+    return _DecAssemble.apply(ctx_tok, mask_token, emb, ids_keep, ids_restore, q_start, n_q, n_glob)
+
+
+# ---------------------------------------------------------------------------------------------
+# out_proj + un-patchify (output_adapters.py:288-294): tokens bf16 [B*N, Dd] -> image fp32 [B,C,H,W]
+# ---------------------------------------------------------------------------------------------
+class _ProjUnpatch(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, geom, save):
+        C_, ph, pw, gh, gw = geom
+        T, K = x.shape
+        img = ops.gemm(x, bf16_weight(weight), m=T, n=weight.shape[0], k=K, bias=bias,
+                       out_dtype=torch.float32, unpatch=geom)
+        if save:
+            ctx.save_for_backward(x, weight)
+            ctx.geom = geom
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        x, weight = ctx.saved_tensors
+        C_, ph, pw, gh, gw = ctx.geom
+        dyb = ops.patchify_cast(dimg.contiguous().float(), ph, pw)          # [T, C*ph*pw] bf16
+        dx = dgrad(dyb, bf16_weight(weight)) if ctx.needs_input_grad[0] else None
+        return dx, wgrad(dyb, x), ops.colsum(dyb), None, None
+
+
+def proj_unpatch(x, weight, bias, geom):
+    return _ProjUnpatch.apply(x, weight, bias, geom, grad_needed(x, weight, bias))
+
+
+# ---------------------------------------------------------------------------------------------
+# masked criteria (criterion.py)
+# ---------------------------------------------------------------------------------------------
+class _MaskedMSE(Function):
+    @staticmethod
+    def forward(ctx, pred, target, mask, scale):
+        pred = pred.contiguous()
+        target = target.contiguous()
+        loss, coef = ops.masked_mse_fwd(pred, target, mask, scale)
+        ctx.save_for_backward(pred, target, mask, coef)
+        ctx.scale = scale
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target, mask, coef = ctx.saved_tensors
+        return ops.masked_mse_bwd(pred, target, mask, coef, g.contiguous().float(), ctx.scale), None, None, None
+
+
+class _MaskedCE(Function):
+    @staticmethod
+    def forward(ctx, logits, target, mask, scale, smoothing):
+        logits = logits.contiguous()
+        target = target.contiguous()
+        loss, coef = ops.masked_ce_fwd(logits, target, mask, scale, smoothing)
+        ctx.save_for_backward(logits, target, mask, coef)
+        ctx.cfg = (scale, smoothing)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target, mask, coef = ctx.saved_tensors
+        scale, smoothing = ctx.cfg
+        return (ops.masked_ce_bwd(logits, target, mask, coef, g.contiguous().float(), scale, smoothing),
+                None, None, None, None)
+
+
+def masked_mse(pred, target, mask, scale):
+    return _MaskedMSE.apply(pred, target, mask, scale)
+
+
+def masked_ce(logits, target, mask, scale, smoothing=0.0):
+    return _MaskedCE.apply(logits, target, mask, scale, smoothing)
+
+
+# one-entry cache: the three output adapters all project the same encoder tokens (K12 in SURVEY.md)
+_last_cast: dict = {}
+
+
+def cached_bf16(x: torch.Tensor) -> torch.Tensor:
+    key = (x.data_ptr(), x._version, tuple(x.shape), x.requires_grad, torch.is_grad_enabled())
+    if _last_cast.get('key') == key and _last_cast.get('src') is not None and _last_cast['src']() is not None:
+        return _last_cast['out']
+    import weakref
+    out = to_bf16(x)
+    _last_cast['key'] = key
+    try:
+        _last_cast['src'] = weakref.ref(x)
+    except TypeError:
+        _last_cast['src'] = None
+    _last_cast['out'] = out
+    return out

@@ -16,6 +16,45 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---------------------------------------------------------------------------------------------
+# launch accounting / per-kernel timing hooks (used by bench.py; zero cost when disabled)
+# ---------------------------------------------------------------------------------------------
+class _Stats:
+    launches = 0          # kernels launched through this module since reset
+    recorder = None       # callable(name, work, unit) -> context manager, or None
+
+
+def reset_launch_count():
+    _Stats.launches = 0
+
+
+def launch_count() -> int:
+    return _Stats.launches
+
+
+def set_recorder(fn):
+    """fn(name: str, work: float, unit: 'flop'|'byte') must return a context manager that brackets
+    the launch (bench.py records CUDA events on the current stream inside it)."""
+    _Stats.recorder = fn
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def _rec(name: str, work: float, unit: str, kernels: int = 1):
+    _Stats.launches += kernels
+    r = _Stats.recorder
+    return _NULL if r is None else r(name, work, unit)
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -35,7 +74,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int,
          dgelu_aux: torch.Tensor | None = None,
          atomic: bool = False, k_splits: int = 1, block_n: int = 0,
          img_hw: tuple[int, int] | None = None,
-         out_row_map: tuple[int, int, int] | None = None) -> torch.Tensor:
+         out_row_map: tuple[int, int, int] | None = None,
+         unpatch: tuple[int, int, int, int, int] | None = None) -> torch.Tensor:
     """out[m, n] = epilogue(A * B^T); see ``mb_gemm`` in include/mirage_b200.h for the contract.
 
     ``a`` / ``b`` are 2-D (or, for MB_A_PATCH32, the [B,1,H,W] fp32 image batch) with unit stride in
@@ -46,7 +86,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int,
     if a.dtype not in (torch.bfloat16, torch.float32) or b.dtype != a.dtype:
         raise L.MirageB200Error(f"gemm: unsupported operand dtypes {a.dtype}, {b.dtype}")
     if out is None:
-        out = torch.empty((m, n), dtype=out_dtype, device=a.device)
+        if unpatch is not None:
+            c_, ph_, pw_, gh_, gw_ = unpatch
+            out = torch.empty((m // (gh_ * gw_), c_, gh_ * ph_, gw_ * pw_), dtype=out_dtype, device=a.device)
+        else:
+            out = torch.empty((m, n), dtype=out_dtype, device=a.device)
     args = L.GemmArgs()
     args.a, args.b, args.out = a.data_ptr(), b.data_ptr(), out.data_ptr()
     args.bias = _ptr(bias)
@@ -63,7 +107,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int,
         args.lda = a.stride(0)
     assert b.stride(-1) == 1 and out.stride(-1) == 1
     args.ldb = b.stride(0)
-    args.ldc = out.stride(0)
+    args.ldc = out.stride(0) if unpatch is None else n
     args.ld_res = residual.stride(0) if residual is not None else 0
     aux = aux_out if aux_out is not None else dgelu_aux
     args.ld_aux = aux.stride(0) if aux is not None else 0
@@ -87,7 +131,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int,
     args.block_n = block_n
     if out_row_map is not None:
         args.out_row_period, args.out_row_stride, args.out_row_offset = out_row_map
-    L.check(L.lib().mb_gemm(C.byref(args), _stream()), "mb_gemm")
+    if unpatch is not None:
+        assert out.is_contiguous()
+        args.epilogue |= L.MB_EPI_UNPATCH
+        args.up_channels, args.up_ph, args.up_pw, args.up_gh, args.up_gw = unpatch
+    with _rec("gemm", 2.0 * m * n * k, "flop"):
+        L.check(L.lib().mb_gemm(C.byref(args), _stream()), "mb_gemm")
     return out
 
 
@@ -108,7 +157,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, 
     a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
     a.head_dim = head_dim
     a.scale = scale
-    L.check(L.lib().mb_attn_fwd(C.byref(a), _stream()), "mb_attn_fwd")
+    with _rec("attn_fwd", 4.0 * batch * heads * nq * nk * head_dim, "flop"):
+        L.check(L.lib().mb_attn_fwd(C.byref(a), _stream()), "mb_attn_fwd")
     return out
 
 
@@ -123,10 +173,11 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: fl
     if save_stats:
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-    L.check(L.lib().mb_layernorm_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(),
-                                     L.MB_BF16 if out_dtype == torch.bfloat16 else L.MB_F32,
-                                     _ptr(mean), _ptr(rstd), rows, dim, x.stride(0), y.stride(0),
-                                     eps, _stream()), "mb_layernorm_fwd")
+    with _rec("layernorm_fwd", rows * dim * (4.0 + y.element_size()), "byte"):
+        L.check(L.lib().mb_layernorm_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(),
+                                         L.MB_BF16 if out_dtype == torch.bfloat16 else L.MB_F32,
+                                         _ptr(mean), _ptr(rstd), rows, dim, x.stride(0), y.stride(0),
+                                         eps, _stream()), "mb_layernorm_fwd")
     return (y, mean, rstd) if save_stats else y
 
 
@@ -139,11 +190,13 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, mean:
     dw = torch.empty(dim, dtype=torch.float32, device=x.device)
     db = torch.empty(dim, dtype=torch.float32, device=x.device)
     ws = torch.empty(L.lib().mb_layernorm_bwd_workspace(rows, dim), dtype=torch.uint8, device=x.device)
-    L.check(L.lib().mb_layernorm_bwd(dy.data_ptr(), L.MB_BF16 if dy.dtype == torch.bfloat16 else L.MB_F32,
-                                     x.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                     _ptr(dres), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), 0,
-                                     ws.data_ptr(), rows, dim, x.stride(0), dy.stride(0), dx.stride(0),
-                                     _stream()), "mb_layernorm_bwd")
+    nbytes = rows * dim * (dy.element_size() + 4.0 + 4.0 + (4.0 if dres is not None else 0.0))
+    with _rec("layernorm_bwd", nbytes, "byte", kernels=2):
+        L.check(L.lib().mb_layernorm_bwd(dy.data_ptr(), L.MB_BF16 if dy.dtype == torch.bfloat16 else L.MB_F32,
+                                         x.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                         _ptr(dres), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), 0,
+                                         ws.data_ptr(), rows, dim, x.stride(0), dy.stride(0), dx.stride(0),
+                                         _stream()), "mb_layernorm_bwd")
     return dx, dw, db
 
 
@@ -153,9 +206,10 @@ def colsum(a: torch.Tensor) -> torch.Tensor:
     rows, cols = a.shape
     out = torch.empty(cols, dtype=torch.float32, device=a.device)
     ws = torch.empty(L.lib().mb_colsum_workspace(rows, cols), dtype=torch.uint8, device=a.device)
-    L.check(L.lib().mb_colsum(a.data_ptr(), L.MB_BF16 if a.dtype == torch.bfloat16 else L.MB_F32,
-                              out.data_ptr(), 0, ws.data_ptr(), rows, cols, a.stride(0), _stream()),
-            "mb_colsum")
+    with _rec("colsum", float(rows * cols * a.element_size()), "byte", kernels=2):
+        L.check(L.lib().mb_colsum(a.data_ptr(), L.MB_BF16 if a.dtype == torch.bfloat16 else L.MB_F32,
+                                  out.data_ptr(), 0, ws.data_ptr(), rows, cols, a.stride(0), _stream()),
+                "mb_colsum")
     return out
 
 
@@ -168,9 +222,10 @@ def token_gather(src: torch.Tensor, ids_keep: torch.Tensor, global_tokens: torch
     assert src.is_contiguous() and ids_keep.is_contiguous() and global_tokens.is_contiguous()
     assert src.dtype == torch.float32 and ids_keep.dtype == torch.int64
     out = torch.empty((B, n_keep + n_glob, D), dtype=torch.float32, device=src.device)
-    L.check(L.lib().mb_token_gather_fwd(src.data_ptr(), ids_keep.data_ptr(), global_tokens.data_ptr(),
-                                        out.data_ptr(), B, n_src, n_keep, n_glob, D, _stream()),
-            "mb_token_gather_fwd")
+    with _rec("token_gather", 8.0 * B * (n_keep + n_glob) * D, "byte"):
+        L.check(L.lib().mb_token_gather_fwd(src.data_ptr(), ids_keep.data_ptr(), global_tokens.data_ptr(),
+                                            out.data_ptr(), B, n_src, n_keep, n_glob, D, _stream()),
+                "mb_token_gather_fwd")
     return out
 
 
@@ -181,9 +236,10 @@ def token_gather_bwd(dout: torch.Tensor, ids_keep: torch.Tensor, n_src: int, n_g
     assert dout.is_contiguous() and dout.dtype == torch.float32
     dsrc = torch.empty((B, n_src, D), dtype=torch.float32, device=dout.device)
     dglob = torch.empty((n_glob, D), dtype=torch.float32, device=dout.device)
-    L.check(L.lib().mb_token_gather_bwd(dout.data_ptr(), ids_keep.data_ptr(), dsrc.data_ptr(),
-                                        dglob.data_ptr(), B, n_src, n_keep, n_glob, D, _stream()),
-            "mb_token_gather_bwd")
+    with _rec("token_scatter", 4.0 * B * (n_src + 2 * n_keep) * D, "byte", kernels=3):
+        L.check(L.lib().mb_token_gather_bwd(dout.data_ptr(), ids_keep.data_ptr(), dsrc.data_ptr(),
+                                            dglob.data_ptr(), B, n_src, n_keep, n_glob, D, _stream()),
+                "mb_token_gather_bwd")
     return dsrc, dglob
 
 
@@ -191,9 +247,10 @@ def fill_global_rows(global_tokens: torch.Tensor, out: torch.Tensor, row_offset:
     """out[:, row_offset:row_offset+n_glob, :] = global_tokens (out is [B, rows_total, D] fp32)."""
     _req_cuda(global_tokens, out)
     B, rows_total, D = out.shape
-    L.check(L.lib().mb_fill_global_rows(global_tokens.data_ptr(), out.data_ptr(), B, rows_total,
-                                        row_offset, global_tokens.shape[0], D, _stream()),
-            "mb_fill_global_rows")
+    with _rec("fill_global_rows", 4.0 * B * global_tokens.shape[0] * D, "byte"):
+        L.check(L.lib().mb_fill_global_rows(global_tokens.data_ptr(), out.data_ptr(), B, rows_total,
+                                            row_offset, global_tokens.shape[0], D, _stream()),
+                "mb_fill_global_rows")
     return out
 
 
@@ -201,6 +258,142 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     _req_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    L.check(L.lib().mb_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()),
-            "mb_cast_f32_to_bf16")
+    with _rec("cast_bf16", 6.0 * x.numel(), "byte"):
+        L.check(L.lib().mb_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()),
+                "mb_cast_f32_to_bf16")
     return out
+
+
+def attention_bwd(q, k, v, out, d_out, lse, dq, dk, dv, *, batch, heads, nq, nk, head_dim, scale):
+    """Writes dq/dk/dv (bf16 views, token-major) given the forward tensors and d_out."""
+    _req_cuda(q, k, v, out, d_out, lse, dq, dk, dv)
+    a = L.AttnBwdArgs()
+    a.q, a.k, a.v, a.out, a.d_out, a.lse = (q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                            d_out.data_ptr(), lse.data_ptr())
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    wsb = L.lib().mb_attn_bwd_workspace(batch, heads, nq, nk, head_dim)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=q.device) if wsb else None
+    a.workspace = _ptr(ws)
+    a.batch, a.heads, a.nq, a.nk = batch, heads, nq, nk
+    a.ldq, a.ldk, a.ldv, a.ldo, a.lddo = q.stride(0), k.stride(0), v.stride(0), out.stride(0), d_out.stride(0)
+    a.lddq, a.lddk, a.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
+    a.head_dim = head_dim
+    a.scale = scale
+    with _rec("attn_bwd", 10.0 * batch * heads * nq * nk * head_dim, "flop"):
+        L.check(L.lib().mb_attn_bwd(C.byref(a), _stream()), "mb_attn_bwd")
+
+
+def semseg_patches(labels: torch.Tensor, class_emb_bf16: torch.Tensor, ph: int, pw: int) -> torch.Tensor:
+    """labels int64 [B,H,W] -> bf16 [B*(H/ph)*(W/pw), E*ph*pw] (embedding lookup + patch extraction)."""
+    _req_cuda(labels, class_emb_bf16)
+    assert labels.dtype == torch.int64 and labels.is_contiguous()
+    B, H, W = labels.shape
+    n_cls, E = class_emb_bf16.shape
+    out = torch.empty((B * (H // ph) * (W // pw), E * ph * pw), dtype=torch.bfloat16, device=labels.device)
+    with _rec("semseg_patches", float(out.numel() * 2 + labels.numel() * 8), "byte"):
+        L.check(L.lib().mb_semseg_patches(labels.data_ptr(), class_emb_bf16.data_ptr(), out.data_ptr(),
+                                          B, H, W, ph, pw, n_cls, E, _stream()), "mb_semseg_patches")
+    return out
+
+
+def class_emb_grad(labels, d_patches_bf16, n_cls: int, E: int, ph: int, pw: int) -> torch.Tensor:
+    _req_cuda(labels, d_patches_bf16)
+    B, H, W = labels.shape
+    out = torch.empty((n_cls, E), dtype=torch.float32, device=labels.device)
+    with _rec("class_emb_grad", float(d_patches_bf16.numel() * 2 + labels.numel() * 8), "byte", kernels=2):
+        L.check(L.lib().mb_class_emb_grad(labels.data_ptr(), d_patches_bf16.data_ptr(), out.data_ptr(),
+                                          B, H, W, ph, pw, n_cls, E, _stream()), "mb_class_emb_grad")
+    return out
+
+
+def dec_assemble(ctx, mask_token, emb, ids_keep, ids_restore, q_start: int, n_q: int, n_glob: int):
+    """ctx f32 [B, n_vis+n_glob, Dd] -> (queries f32 [B, n_q, Dd], context f32 [B, n_vis+n_glob, Dd])."""
+    _req_cuda(ctx, mask_token, emb, ids_keep, ids_restore)
+    B, n_ctx, Dd = ctx.shape
+    n_vis = n_ctx - n_glob
+    n_all = ids_restore.shape[1]
+    q = torch.empty((B, n_q, Dd), dtype=torch.float32, device=ctx.device)
+    c = torch.empty((B, n_ctx, Dd), dtype=torch.float32, device=ctx.device)
+    with _rec("dec_assemble", 4.0 * Dd * B * (2 * n_q + 2 * n_ctx), "byte"):
+        L.check(L.lib().mb_dec_assemble_fwd(ctx.data_ptr(), mask_token.data_ptr(), emb.data_ptr(),
+                                            ids_keep.data_ptr(), ids_restore.data_ptr(), q.data_ptr(),
+                                            c.data_ptr(), B, n_vis, n_glob, n_all, q_start, n_q, Dd,
+                                            _stream()), "mb_dec_assemble_fwd")
+    return q, c
+
+
+def dec_assemble_bwd(dq, dc, ids_keep, ids_restore, q_start: int, n_glob: int):
+    _req_cuda(dq, dc, ids_keep, ids_restore)
+    B, n_q, Dd = dq.shape
+    n_ctx = dc.shape[1]
+    n_vis = n_ctx - n_glob
+    n_all = ids_restore.shape[1]
+    dctx = torch.empty((B, n_ctx, Dd), dtype=torch.float32, device=dq.device)
+    demb = torch.empty((n_all, Dd), dtype=torch.float32, device=dq.device)
+    dmask = torch.empty((Dd,), dtype=torch.float32, device=dq.device)
+    ws = torch.empty((n_q, Dd), dtype=torch.float32, device=dq.device)
+    with _rec("dec_assemble_bwd", 4.0 * Dd * B * (2 * n_q + 3 * n_ctx), "byte", kernels=3):
+        L.check(L.lib().mb_dec_assemble_bwd(dq.data_ptr(), dc.data_ptr(), ids_keep.data_ptr(),
+                                            ids_restore.data_ptr(), dctx.data_ptr(), demb.data_ptr(),
+                                            dmask.data_ptr(), ws.data_ptr(), B, n_vis, n_glob, n_all,
+                                            q_start, n_q, Dd, _stream()), "mb_dec_assemble_bwd")
+    return dctx, demb, dmask
+
+
+def patchify_cast(img: torch.Tensor, ph: int, pw: int) -> torch.Tensor:
+    """f32 [B,C,H,W] -> bf16 [B*(H/ph)*(W/pw), C*ph*pw]."""
+    _req_cuda(img)
+    assert img.dtype == torch.float32 and img.is_contiguous()
+    B, Cc, H, W = img.shape
+    gh, gw = H // ph, W // pw
+    out = torch.empty((B * gh * gw, Cc * ph * pw), dtype=torch.bfloat16, device=img.device)
+    with _rec("patchify_cast", 6.0 * img.numel(), "byte"):
+        L.check(L.lib().mb_patchify_cast(img.data_ptr(), out.data_ptr(), B, Cc, ph, pw, gh, gw, _stream()),
+                "mb_patchify_cast")
+    return out
+
+
+def masked_mse_fwd(pred, target, mask, scale: int):
+    _req_cuda(pred, target, mask)
+    B, Cc, H, W = pred.shape
+    loss = torch.empty((), dtype=torch.float32, device=pred.device)
+    coef = torch.empty((B,), dtype=torch.float32, device=pred.device)
+    ws = torch.empty(L.lib().mb_masked_loss_workspace(B, H, W), dtype=torch.uint8, device=pred.device)
+    with _rec("masked_mse_fwd", 8.0 * pred.numel(), "byte", kernels=2):
+        L.check(L.lib().mb_masked_mse_fwd(pred.data_ptr(), target.data_ptr(), _ptr(mask), loss.data_ptr(),
+                                          coef.data_ptr(), ws.data_ptr(), B, Cc, H, W, scale, _stream()),
+                "mb_masked_mse_fwd")
+    return loss, coef
+
+
+def masked_mse_bwd(pred, target, mask, coef, gout, scale: int):
+    B, Cc, H, W = pred.shape
+    dpred = torch.empty_like(pred)
+    with _rec("masked_mse_bwd", 12.0 * pred.numel(), "byte"):
+        L.check(L.lib().mb_masked_mse_bwd(pred.data_ptr(), target.data_ptr(), _ptr(mask), coef.data_ptr(),
+                                          gout.data_ptr(), dpred.data_ptr(), B, Cc, H, W, scale, _stream()),
+                "mb_masked_mse_bwd")
+    return dpred
+
+
+def masked_ce_fwd(logits, target, mask, scale: int, smoothing: float):
+    _req_cuda(logits, target, mask)
+    B, Cc, H, W = logits.shape
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    coef = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    ws = torch.empty(L.lib().mb_masked_loss_workspace(B, H, W), dtype=torch.uint8, device=logits.device)
+    with _rec("masked_ce_fwd", 4.0 * logits.numel() + 8.0 * target.numel(), "byte", kernels=2):
+        L.check(L.lib().mb_masked_ce_fwd(logits.data_ptr(), target.data_ptr(), _ptr(mask), loss.data_ptr(),
+                                         coef.data_ptr(), ws.data_ptr(), B, Cc, H, W, scale, smoothing,
+                                         _stream()), "mb_masked_ce_fwd")
+    return loss, coef
+
+
+def masked_ce_bwd(logits, target, mask, coef, gout, scale: int, smoothing: float):
+    B, Cc, H, W = logits.shape
+    dl = torch.empty_like(logits)
+    with _rec("masked_ce_bwd", 8.0 * logits.numel() + 8.0 * target.numel(), "byte"):
+        L.check(L.lib().mb_masked_ce_bwd(logits.data_ptr(), target.data_ptr(), _ptr(mask), coef.data_ptr(),
+                                         gout.data_ptr(), dl.data_ptr(), B, Cc, H, W, scale, smoothing,
+                                         _stream()), "mb_masked_ce_bwd")
+    return dl

@@ -1,0 +1,109 @@
+"""The CPU oracle (oracle/mirage_oracle.py) against the golden vectors produced by the unmodified
+reference (oracle/make_golden.py).  Runs without a GPU; this is what pins the oracle."""
+import torch
+
+from helpers import GOLDEN, synth_images, synth_state_dict
+from oracle import mirage_oracle as O
+from pretrain_case import MODS, SIZES, build_pretrain_model, oracle_step
+
+
+def _check_sub(got: torch.Tensor, gold: dict, rtol: float, atol: float = 0.0):
+    assert tuple(got.shape) == tuple(gold["shape"])
+    f = got.detach().float().reshape(-1, got.shape[-1])
+    rows = f[:: gold["step"]]
+    scale = gold["rows"].abs().max().item() + 1e-12
+    assert (rows - gold["rows"]).abs().max().item() <= rtol * scale + atol
+    assert abs(f.double().sum().item() - gold["sum"]) <= rtol * (gold["abs_sum"] + 1e-9)
+    assert abs(f.double().abs().sum().item() - gold["abs_sum"]) <= rtol * (gold["abs_sum"] + 1e-9)
+
+
+def _encoder_sd(size):
+    from mirage_b200.mirage_hf import MIRAGEWrapper
+    m = MIRAGEWrapper(size=size)
+    sd = m.model.state_dict()
+    sd.update(synth_state_dict({k: v.shape for k, v in sd.items()}, 0))
+    return sd
+
+
+def test_sincos_posemb_matches_host_module():
+    from mirage_b200.utils import build_2d_sincos_posemb
+    for (h, w, d) in [(16, 16, 768), (16, 16, 256), (8, 12, 64)]:
+        assert torch.equal(O.sincos_posemb_2d(h, w, d), build_2d_sincos_posemb(h, w, d))
+
+
+def test_encoder_base_golden():
+    g = torch.load(GOLDEN / "encoder_base.pt")
+    x = synth_images(g["batch"], ["bscan", "slo"], seed=g["input_seed"])
+    with torch.no_grad():
+        out = O.light_forward(x, _encoder_sd("base"), 12, 12)
+    _check_sub(out, g["out"], 2e-5)
+
+
+def test_encoder_large_golden():
+    g = torch.load(GOLDEN / "encoder_large.pt")
+    x = synth_images(g["batch"], ["bscan", "slo"], seed=g["input_seed"])
+    with torch.no_grad():
+        out = O.light_forward(x, _encoder_sd("large"), 24, 16)
+    _check_sub(out, g["out"], 2e-5)
+
+
+def test_random_masks_bit_exact():
+    g = torch.load(GOLDEN / "masks.pt")
+    for case in g["cases"]:
+        torch.manual_seed(case["seed"])
+        tm, keep, restore = O.random_masks(g["counts"], case["B"], case["n_vis"], alphas=case["alphas"])
+        assert torch.equal(keep, case["ids_keep"].long())
+        assert torch.equal(restore, case["ids_restore"].long())
+        for d, m in zip(g["domains"], tm):
+            assert torch.equal(m, case["task_masks"][d].long())
+        # invariants the reference guarantees
+        assert int(sum(int((m == 0).sum()) for m in tm)) == case["B"] * case["n_vis"]
+        assert torch.equal(torch.gather(restore, 1, keep),
+                           torch.arange(case["n_vis"]).expand(case["B"], -1))
+
+
+def test_criterion_golden():
+    g = torch.load(GOLDEN / "criterion.pt")
+    gen = torch.Generator().manual_seed(g["seed"])
+    B = g["B"]
+    pred = torch.randn(B, 1, 512, 512, generator=gen)
+    tgt = torch.rand(B, 1, 512, 512, generator=gen)
+    logits = torch.randn(B, 13, 128, 128, generator=gen)
+    labels = torch.randint(0, 13, (B, 128, 128), generator=gen)
+    for k in g["mse"]:
+        m = None if k == "no_mask" else g["masks"][k].long()
+        assert abs(float(O.masked_mse(pred, tgt, m, 32)) - g["mse"][k]) <= 1e-5 * max(1.0, abs(g["mse"][k]))
+        assert abs(float(O.masked_ce(logits, labels, m, 8)) - g["ce"][k]) <= 1e-5 * max(1.0, abs(g["ce"][k]))
+        assert abs(float(O.masked_ce(logits, labels, m, 8, 0.1)) - g["ce_ls"][k]) <= 1e-5 * max(1.0, abs(g["ce_ls"][k]))
+
+
+def _pretrain_golden(tag):
+    g = torch.load(GOLDEN / f"pretrain_{tag}.pt")
+    assert (g["dim"], g["depth"], g["heads"]) == SIZES[tag]
+    model, _ = build_pretrain_model(tag)
+    sd = model.state_dict()
+    sd.update(synth_state_dict({k: v.shape for k, v in sd.items()}, g["weights_seed"]))
+    x = synth_images(g["batch"], MODS, seed=g["input_seed"])
+    masks = ({k: v.long() for k, v in g["task_masks"].items()}, g["ids_keep"].long(), g["ids_restore"].long())
+    preds, losses, grads = oracle_step(sd, x, masks, tag)
+    for d in MODS:
+        assert abs(losses[d] - g["losses"][d]) <= 2e-5 * abs(g["losses"][d]), (d, losses[d], g["losses"][d])
+        _check_sub(preds[d], g["preds"][d], 5e-5)
+    assert set(grads) == set(g["grad_norm"])
+    for k, n in g["grad_norm"].items():
+        assert abs(grads[k].norm().item() - n) <= 1e-3 * n + 1e-7, (k, grads[k].norm().item(), n)
+    for k, t in g["grad_small"].items():
+        assert (grads[k] - t).abs().max().item() <= 1e-3 * (t.abs().max().item() + 1e-9) + 1e-8, k
+    for k, sub in g["grad_big"].items():
+        gk = grads[k]
+        _check_sub(gk.reshape(-1, gk.shape[-1]) if gk.dim() > 1 else gk.reshape(1, -1),
+                   {**sub, "shape": tuple((gk.reshape(-1, gk.shape[-1]) if gk.dim() > 1 else gk.reshape(1, -1)).shape)},
+                   2e-3, atol=1e-8)  # atol: gradients that are analytically zero (key bias) are pure noise
+
+
+def test_pretrain_tiny_golden():
+    _pretrain_golden("tiny")
+
+
+def test_pretrain_base_golden():
+    _pretrain_golden("base")
