@@ -1,0 +1,73 @@
+"""Pretraining workloads for bench.py (cfg 3 / cfg 4 of BASELINE.json): model + criteria + AdamW +
+gradient all-reduce on the GPU arm, and the oracle's forward+backward on the CPU arm."""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def build_pretrain_step(size, mods, per_gpu, dev, rank, world):
+    from helpers import load_synth, synth_images
+    from mirage_b200.ddp import GradBucketAllReduce
+    from pretrain_case import build_criteria, build_pretrain_model
+
+    model, _ = build_pretrain_model(size, mods)
+    load_synth(model, seed=3)
+    model = model.to(dev).train()
+    crits = build_criteria(mods)
+    ddp = GradBucketAllReduce(model, bucket_mb=64)
+    decay, no_decay = [], []
+    skip = model.no_weight_decay()
+    for n, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        (no_decay if (p.ndim <= 1 or n.endswith(".bias") or n in skip) else decay).append(p)
+    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}],
+                            lr=1e-4 * per_gpu * world / 256, betas=(0.9, 0.95), fused=True)
+
+    base = synth_images(8, mods, seed=1234 + rank)
+    reps = per_gpu // 8 + 1
+    host_in = {k: v.repeat(reps, *([1] * (v.dim() - 1)))[:per_gpu].contiguous().pin_memory() for k, v in base.items()}
+    dev_in = {k: v.to(dev) for k, v in host_in.items()}
+    torch.manual_seed(100 + rank)
+    host_loss = torch.zeros(1).pin_memory()
+
+    def one_step(x):
+        ddp.zero_grad()
+        preds, masks = model(x, num_encoded_tokens=98, alphas=1.0, sample_tasks_uniformly=False)
+        loss = sum(crits[d](preds[d].float(), x[d], mask=masks[d]) for d in mods)
+        loss.backward()
+        ddp.finish()
+        opt.step()
+        return loss
+
+    def step():
+        return one_step(dev_in)
+
+    def step_e2e():
+        x = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
+        loss = one_step(x)
+        host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss
+
+    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+    return step, step_e2e, h2d, 4
+
+
+def build_pretrain_oracle(size, mods, batch, seed):
+    from helpers import synth_images, synth_state_dict
+    from pretrain_case import build_pretrain_model, oracle_step, sample_masks
+    model, _ = build_pretrain_model(size, mods)
+    sd = model.state_dict()
+    sd.update(synth_state_dict({k: v.shape for k, v in sd.items()}, 3))
+    x = synth_images(batch, mods, seed=1234)
+    masks = sample_masks(model, batch, 98, seed=100)
+
+    def run():
+        return oracle_step(sd, x, masks, size, mods)
+    return run

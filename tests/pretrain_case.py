@@ -101,7 +101,7 @@ def run_pretrain_parity(dev, size="tiny", batch=2, verbose=False):
     torch.cuda.synchronize()
     out = {"loss_rel": 0.0, "pred_max_rel": 0.0, "pred_min_cos": 1.0, "grad_max_rel_fro": 0.0, "grad_min_cos": 1.0}
     for d in MODS:
-        m = parity(p[d].permute(0, 2, 3, 1), p_ref[d].permute(0, 2, 3, 1))
+        m = parity(p[d].reshape(-1, p[d].shape[-1]), p_ref[d].reshape(-1, p_ref[d].shape[-1]))  # rows = image rows
         out["pred_max_rel"] = max(out["pred_max_rel"], m["max_rel"])
         out["pred_min_cos"] = min(out["pred_min_cos"], m["min_cos"])
         out["loss_rel"] = max(out["loss_rel"], abs(l[d] - l_ref[d]) / abs(l_ref[d]))
