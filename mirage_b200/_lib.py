@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("out_row_period", C.c_int64), ("out_row_stride", C.c_int64), ("out_row_offset", C.c_int64),
         ("up_channels", C.c_int32), ("up_ph", C.c_int32), ("up_pw", C.c_int32),
         ("up_gh", C.c_int32), ("up_gw", C.c_int32),
+        ("cta_pair", C.c_int32),
     ]
 
 

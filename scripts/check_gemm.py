@@ -150,6 +150,51 @@ def group_patch():
     return ok
 
 
+def group_pair():
+    """cta_group::2 kernel (forced): every layout / epilogue the 1-CTA kernel supports."""
+    ok = True
+    for (m, n, k, bn) in [(256, 256, 64, 256), (256, 256, 256, 256), (512, 512, 1024, 256), (256, 128, 128, 128),
+                          (4096, 1024, 1024, 256), (4096, 1024, 1024, 128), (1539, 832, 256, 128),
+                          (693, 768, 768, 256), (131328, 1024, 1024, 256)]:
+        a, w = mk(m, k), mk(n, k, scale=k ** -0.5)
+        out = ops.gemm(a, w, m=m, n=n, k=k, block_n=bn, cta_pair=2)
+        ok &= report(f"pair fwd m={m} n={n} k={k} bn={bn}", out, a.float() @ w.float().t())
+    m, n, k = 1000, 512, 256
+    a, w = mk(m, k), mk(n, k, scale=k ** -0.5)
+    bias, res = torch.randn(n, device=dev), torch.randn(m, n, device=dev)
+    base = a.float() @ w.float().t()
+    pre = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+    out = ops.gemm(a, w, m=m, n=n, k=k, bias=bias, gelu=True, aux_out=pre, cta_pair=2)
+    ok &= report("pair bias+gelu", out, torch.nn.functional.gelu(base + bias))
+    ok &= report("pair gelu aux_out", pre, base + bias)
+    x = res.clone()
+    ops.gemm(a, w, m=m, n=n, k=k, bias=bias, residual=x, out=x, cta_pair=2)
+    ok &= report("pair bias+residual in place", x, base + bias + res, tol=5e-3)
+    for (m, n_out, k_in) in [(256, 128, 256), (1000, 768, 512), (4096, 4096, 1024)]:
+        dy, w = mk(m, n_out), mk(n_out, k_in, scale=n_out ** -0.5)
+        out = ops.gemm(dy, w, m=m, n=k_in, k=n_out, b_layout=L.MB_MAJOR_MN, cta_pair=2)
+        ok &= report(f"pair dgrad m={m} n_out={n_out} k_in={k_in}", out, dy.float() @ w.float())
+    for (t, n_out, k_in, splits) in [(64, 256, 256, 1), (1000, 768, 512, 1), (4096, 1024, 1024, 8),
+                                     (25344, 1024, 4096, 4)]:
+        dy, x = mk(t, n_out, scale=t ** -0.5), mk(t, k_in)
+        out = torch.zeros(n_out, k_in, device=dev)
+        ops.gemm(dy, x, m=n_out, n=k_in, k=t, a_layout=L.MB_MAJOR_MN, b_layout=L.MB_MAJOR_MN, out=out,
+                 k_splits=splits, atomic=True, cta_pair=2)
+        ok &= report(f"pair wgrad t={t} n_out={n_out} k_in={k_in} splits={splits}", out,
+                     dy.float().t() @ x.float(), tol=1e-2)
+    for (b, d) in [(2, 256), (8, 1024)]:
+        img = torch.rand(b, 1, 512, 512, device=dev)
+        w = torch.randn(d, 1, 32, 32, device=dev) * 0.03
+        bias = torch.randn(d, device=dev) * 0.1
+        pos = torch.randn(256, d, device=dev)
+        out = ops.gemm(img, w.view(d, 1024), m=b * 256, n=d, k=1024, a_layout=L.MB_A_PATCH32,
+                       img_hw=(512, 512), bias=bias, residual=pos, res_period=256,
+                       out_dtype=torch.float32, cta_pair=2)
+        ref = torch.nn.functional.conv2d(img, w, bias, stride=32).flatten(2).transpose(1, 2) + pos
+        ok &= report(f"pair patch32 tf32 b={b} d={d}", out, ref.flatten(0, 1), tol=5e-3)
+    return ok
+
+
 def group_perf():
     shapes = [(131328, 3072, 1024), (131328, 1024, 1024), (131328, 4096, 1024), (131328, 1024, 4096),
               (25344, 4096, 1024), (8192, 8192, 8192)]
@@ -157,17 +202,20 @@ def group_perf():
         a, w = mk(m, k), mk(n, k, scale=k ** -0.5)
         bias = torch.randn(n, device=dev)
         out = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
-        for _ in range(3):
-            ops.gemm(a, w, m=m, n=n, k=k, bias=bias, out=out)
-        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         iters = 10
-        e0.record()
-        for _ in range(iters):
-            ops.gemm(a, w, m=m, n=n, k=k, bias=bias, out=out)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
+        res = {}
+        for mode in (1, 2):
+            for _ in range(3):
+                ops.gemm(a, w, m=m, n=n, k=k, bias=bias, out=out, cta_pair=mode)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                ops.gemm(a, w, m=m, n=n, k=k, bias=bias, out=out, cta_pair=mode)
+            e1.record()
+            torch.cuda.synchronize()
+            res[mode] = e0.elapsed_time(e1) / iters
+        ms = res[2]
         tf = 2.0 * m * n * k / ms / 1e9
         for _ in range(3):
             torch.nn.functional.linear(a, w)
@@ -178,7 +226,8 @@ def group_perf():
         e1.record()
         torch.cuda.synchronize()
         ms_t = e0.elapsed_time(e1) / iters
-        print(f"[PERF] m={m} n={n} k={k}: mb_gemm {ms:.3f} ms = {tf:.0f} TFLOP/s | "
+        print(f"[PERF] m={m} n={n} k={k}: 1-CTA {res[1]:.3f} ms = {2.0 * m * n * k / res[1] / 1e9:.0f} TFLOP/s | "
+              f"pair {ms:.3f} ms = {tf:.0f} TFLOP/s | "
               f"cuBLAS {ms_t:.3f} ms = {2.0 * m * n * k / ms_t / 1e9:.0f} TFLOP/s", flush=True)
     return True
 
