@@ -5,19 +5,25 @@
 // Replaces F.scaled_dot_product_attention + the transpose/reshape copy at
 //   mirage/utils.py:181-185 (Attention)  and  mirage/utils.py:216-220 (CrossAttention).
 //
-// One CTA owns up to TWO 128-row query tiles of one (batch, head) and walks the keys in blocks of
-// 128 (the last block is shortened to a multiple of 16 keys).
+// Persistent CTAs (one per SM) walk work items = (batch, head, pair of 128-row query tiles); within an
+// item the keys are walked in blocks of 128 (the last block is shortened to a multiple of 16 keys).
+// The TMA producer and the MMA warp run ahead into the next item while the softmax warps finish the
+// current one, so there is no per-item pipeline fill bubble.
 //
 //   warp 0      TMA producer: Q tiles once, then K_j / V_j through a 3-stage ring
-//   warp 1      TMEM allocator + MMA issuer (one lane):
+//   warp 1      TMEM allocator + MMA issuer (one lane; warps 2-3 idle; the whole warpgroup gives its
+//               registers to the softmax warps with setmaxnreg):
 //                   S_g = Q_g K_j^T      (SS, both K-major,      accumulator S_g in TMEM)
 //                   O_g += P_g V_j       (SS, P K-major from smem, V MN-major, accumulator O_g)
-//   warps 2-5   softmax group 0 (one thread per query row, no shuffles)
-//   warps 6-9   softmax group 1
+//   warps 4-7   softmax group 0 (one thread per query row, no shuffles, 224 registers)
+//   warps 8-11  softmax group 1
 //
-// The two groups ping-pong: while group 0 exponentiates S_0(j+1) the tensor core runs P_1 V_j and
-// S_1(j+1).  Softmax runs in the log2 domain with a running max m and sum l per row; O is rescaled
-// in TMEM (tcgen05.ld / st) only when some row max in the warp actually moved.
+// Each softmax thread pulls its whole S row (128 fp32) into registers with one round of tcgen05.ld and
+// releases the TMEM buffer at once (s_free), so the MMA warp can already run S_g(j+1) while the row is
+// being exponentiated; the MMA warp is an event-driven scheduler polling {s_free, p_full} of both
+// groups, so neither group ever waits for the other.  Softmax runs in the log2 domain with a running
+// max m and sum l per row (packed FFMA2/FADD2, masking only in the ragged last key block); O is
+// rescaled in TMEM (tcgen05.ld / st) only when some row max in the warp actually moved.
 //
 // TMEM columns: S_0 [0,128)  S_1 [128,256)  O_0 [256,256+HD)  O_1 [320,320+HD).
 #include "../../include/mirage_b200.h"
@@ -34,7 +40,7 @@ struct AttnDev {
   float scale_log2;
 };
 
-constexpr int kAttnThreads = 320;
+constexpr int kAttnThreads = 384;  // 3 warpgroups: {TMA, MMA, -, -}, softmax group 0, softmax group 1
 constexpr int kKvStages = 3;
 
 template <int HD>
@@ -69,7 +75,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* s_full = bars + 13;               // 2
   uint64_t* p_full = bars + 15;               // 2
   uint64_t* o_full = bars + 17;               // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* s_free = bars + 19;               // 2
+  uint64_t* q_empty = bars + 21;              // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -79,19 +87,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     __trap();
   }
 
-  // work decode
-  const int pair = blockIdx.x % p.q_pairs;
-  const int bh = blockIdx.x / p.q_pairs;
-  const int h = bh % p.H;
-  const int b = bh / p.H;
-  const int n_groups = (pair * 2 + 1 < p.q_tiles) ? 2 : 1;
   const int kvb = p.kv_blocks;
+  const int n_items = p.B * p.H * p.q_pairs;  // work item = (batch, head, pair of query tiles)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int s = 0; s < kKvStages; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -102,6 +106,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&s_full[g], 1);
       mbar_init(&p_full[g], 128);
       mbar_init(&o_full[g], 1);
+      mbar_init(&s_free[g], 128);
     }
     mbar_fence_init();
   }
@@ -114,116 +119,194 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
-    // ---------------------------------------------------------------- TMA producer
-    mbar_arrive_expect_tx(q_full, n_groups * Cfg::kTileBytes);
-    for (int g = 0; g < n_groups; ++g)
-      tma_load_3d(smem + Cfg::kOffQ + g * Cfg::kTileBytes, &tm_q, q_full, h * HD,
-                  (pair * 2 + g) * 128, b);
-    for (int j = 0; j < kvb; ++j) {
-      const int s = j % kKvStages;
-      const uint32_t ph = (j / kKvStages) & 1;
-      mbar_wait(&k_empty[s], ph ^ 1);
-      mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
-      tma_load_3d(smem + Cfg::kOffK + s * Cfg::kTileBytes, &tm_k, &k_full[s], h * HD, j * 128, b);
-      mbar_wait(&v_empty[s], ph ^ 1);
-      mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
-      tma_load_3d(smem + Cfg::kOffV + s * Cfg::kTileBytes, &tm_v, &v_full[s], h * HD, j * 128, b);
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ---------------------------------------------------------------- MMA issuer
-    const uint32_t q_addr = smem_u32(smem + Cfg::kOffQ);
-    const uint32_t k_addr = smem_u32(smem + Cfg::kOffK);
-    const uint32_t v_addr = smem_u32(smem + Cfg::kOffV);
-    const uint32_t p_addr = smem_u32(smem + Cfg::kOffP);
-    constexpr uint32_t idesc_pv = make_idesc(128, HD, kFmtBF16, 0, 1);
+  // Persistent CTA: every role walks the same static list of work items; all barrier phases are
+  // tracked with running counters, so the producer / MMA warp run ahead into the next item while the
+  // softmax warps are still finishing the current one.
+  if (warp < 4) {
+    // registers of this warpgroup go to the softmax warpgroups (a whole 128-wide S row lives there)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0 && lane == 0) {
+      // -------------------------------------------------------------- TMA producer
+      int kv_count = 0, item_i = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i) {
+        const int pair = item % p.q_pairs;
+        const int bh = item / p.q_pairs;
+        const int h = bh % p.H, b = bh / p.H;
+        const int n_groups = (pair * 2 + 1 < p.q_tiles) ? 2 : 1;
+        mbar_wait(q_empty, (item_i & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, n_groups * Cfg::kTileBytes);
+        for (int g = 0; g < n_groups; ++g)
+          tma_load_3d(smem + Cfg::kOffQ + g * Cfg::kTileBytes, &tm_q, q_full, h * HD,
+                      (pair * 2 + g) * 128, b);
+        for (int j = 0; j < kvb; ++j, ++kv_count) {
+          const int s = kv_count % kKvStages;
+          const uint32_t ph = (kv_count / kKvStages) & 1;
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
+          tma_load_3d(smem + Cfg::kOffK + s * Cfg::kTileBytes, &tm_k, &k_full[s], h * HD, j * 128, b);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
+          tma_load_3d(smem + Cfg::kOffV + s * Cfg::kTileBytes, &tm_v, &v_full[s], h * HD, j * 128, b);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // -------------------------------------------------------------- MMA issuer
+      // One thread, blocking waits in the order the events occur when the two softmax groups
+      // ping-pong half a block apart:
+      //   S_0(0) S_1(0);  for j: { S_0(j+1), S_1(j+1)  (S buffer released: softmax holds the row in
+      //   registers);  P_0 V(j), P_1 V(j)  (P tile written) }
+      // (a polling scheduler over mbarrier.test_wait lost ~1000 clk per event to test_wait latency).
+      const uint32_t q_addr = smem_u32(smem + Cfg::kOffQ);
+      const uint32_t k_addr = smem_u32(smem + Cfg::kOffK);
+      const uint32_t v_addr = smem_u32(smem + Cfg::kOffV);
+      const uint32_t p_addr = smem_u32(smem + Cfg::kOffP);
+      constexpr uint32_t idesc_pv = make_idesc(128, HD, kFmtBF16, 0, 1);
+      int sc[2] = {0, 0};  // running count of S MMAs per group (phase of s_full / s_free)
+      int pc[2] = {0, 0};  // running count of PV MMAs per group (phase of p_full / o_full)
+      int kv_base = 0;     // running key-block counter at the start of the item (ring slot / phase)
+      int item_i = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i, kv_base += kvb) {
+        const int pair = item % p.q_pairs;
+        const int n_groups = (pair * 2 + 1 < p.q_tiles) ? 2 : 1;
 
-    auto issue_s = [&](int g, int j) {
-      const int s = j % kKvStages;
-      const int valid = min(128, p.Nk - j * 128);
-      const uint32_t ncols = static_cast<uint32_t>((valid + 15) & ~15);
-      const uint32_t idesc_s = make_idesc(128, ncols, kFmtBF16, 0, 0);
-      const uint32_t qa = q_addr + g * Cfg::kTileBytes;
-      const uint32_t ka = k_addr + s * Cfg::kTileBytes;
+        auto issue_s = [&](int g, int j) {
+          const int kc = kv_base + j;
+          if (sc[g] > 0) mbar_wait(&s_free[g], (sc[g] - 1) & 1);
+          if (g == 0) mbar_wait(&k_full[kc % kKvStages], (kc / kKvStages) & 1);
+          tc_fence_after();
+          const int valid = min(128, p.Nk - j * 128);
+          const uint32_t idesc_s = make_idesc(128, static_cast<uint32_t>((valid + 15) & ~15), kFmtBF16, 0, 0);
+          const uint32_t qa = q_addr + g * Cfg::kTileBytes;
+          const uint32_t ka = k_addr + (kc % kKvStages) * Cfg::kTileBytes;
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k) {
-        const uint64_t da = make_smem_desc(qa + k * 32, 0, kSbo, kSw);
-        const uint64_t db = make_smem_desc(ka + k * 32, 0, kSbo, kSw);
-        umma_f16_ss(tmem_base + g * 128, da, db, idesc_s, k > 0 ? 1u : 0u);
-      }
-      umma_commit(&s_full[g]);
-      if (g == n_groups - 1) umma_commit(&k_empty[s]);
-    };
-
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    for (int g = 0; g < n_groups; ++g) issue_s(g, 0);
-
-    for (int j = 0; j < kvb; ++j) {
-      const int s = j % kKvStages;
-      const int valid = min(128, p.Nk - j * 128);
-      const int ksteps = (valid + 15) >> 4;
-      for (int g = 0; g < n_groups; ++g) {
-        mbar_wait(&p_full[g], j & 1);
-        if (g == 0) mbar_wait(&v_full[s], (j / kKvStages) & 1);
-        tc_fence_after();
-        const uint32_t pa = p_addr + g * Cfg::kPBytes;
-        const uint32_t va = v_addr + s * Cfg::kTileBytes;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t da = make_smem_desc(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
-          const uint64_t db = make_smem_desc(va + kk * 16 * Cfg::kRowBytes, 0, kSbo, kSw);
-          umma_f16_ss(tmem_base + 256 + g * 64, da, db, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-        }
-        umma_commit(&o_full[g]);
-        if (g == n_groups - 1) umma_commit(&v_empty[s]);
-        if (j + 1 < kvb) {
-          if (g == 0) {
-            mbar_wait(&k_full[(j + 1) % kKvStages], ((j + 1) / kKvStages) & 1);
-            tc_fence_after();
+          for (int k = 0; k < HD / 16; ++k)
+            umma_f16_ss(tmem_base + g * 128, make_smem_desc(qa + k * 32, 0, kSbo, kSw),
+                        make_smem_desc(ka + k * 32, 0, kSbo, kSw), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+          ++sc[g];
+          if (g == n_groups - 1) {
+            umma_commit(&k_empty[kc % kKvStages]);   // both groups' S(j) are issued
+            if (j == kvb - 1) umma_commit(q_empty);  // last S of the item: the Q tiles may go
           }
-          issue_s(g, j + 1);
+        };
+        auto issue_pv = [&](int g, int j) {
+          const int kc = kv_base + j;
+          mbar_wait(&p_full[g], pc[g] & 1);
+          if (g == 0) mbar_wait(&v_full[kc % kKvStages], (kc / kKvStages) & 1);
+          tc_fence_after();
+          const int valid = min(128, p.Nk - j * 128);
+          const int ksteps = (valid + 15) >> 4;
+          const uint32_t pa = p_addr + g * Cfg::kPBytes;
+          const uint32_t va = v_addr + (kc % kKvStages) * Cfg::kTileBytes;
+          for (int kk = 0; kk < ksteps; ++kk)
+            umma_f16_ss(tmem_base + 256 + g * 64,
+                        make_smem_desc(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+                        make_smem_desc(va + kk * 16 * Cfg::kRowBytes, 0, kSbo, kSw), idesc_pv,
+                        (j > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&o_full[g]);
+          ++pc[g];
+          if (g == n_groups - 1) umma_commit(&v_empty[kc % kKvStages]);
+        };
+
+        mbar_wait(q_full, item_i & 1);
+        for (int g = 0; g < n_groups; ++g) issue_s(g, 0);
+        for (int j = 0; j < kvb; ++j) {
+          if (j + 1 < kvb)
+            for (int g = 0; g < n_groups; ++g) issue_s(g, j + 1);
+          for (int g = 0; g < n_groups; ++g) issue_pv(g, j);
         }
       }
     }
-  } else if (warp >= 2) {
+  } else {
     // ---------------------------------------------------------------- softmax / epilogue
-    const int g = (warp - 2) >> 2;
-    if (g < n_groups) {
-      const int quarter = warp & 3;
-      const int r = quarter * 32 + lane;                    // row inside the tile == TMEM lane
-      const int qrow = (pair * 2 + g) * 128 + r;            // query index inside this (b, h)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int g = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                    // row inside the tile == TMEM lane
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * 128;
+    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256 + g * 64;
+    uint8_t* p_row = smem + Cfg::kOffP + g * Cfg::kPBytes + r * 128;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    int cnt = 0;  // running count of key blocks this group has processed (barrier phases)
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int pair = item % p.q_pairs;
+      const int bh = item / p.q_pairs;
+      const int h = bh % p.H, b = bh / p.H;
+      if (pair * 2 + g >= p.q_tiles) continue;            // this group has no tile in the item
+      const int qrow = (pair * 2 + g) * 128 + r;          // query index inside this (b, h)
       const bool warp_live = (pair * 2 + g) * 128 + quarter * 32 < p.Nq;
-      const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * 128;
-      const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256 + g * 64;
-      uint8_t* p_row = smem + Cfg::kOffP + g * Cfg::kPBytes + r * 128;
-      const uint32_t sw = static_cast<uint32_t>(r & 7);
       float m_run = -INFINITY;
       float l_run = 0.f;
 
-      for (int j = 0; j < kvb; ++j) {
+      for (int j = 0; j < kvb; ++j, ++cnt) {
         const int valid = min(128, p.Nk - j * 128);
         const int nchunks = (valid + 31) >> 5;
-        mbar_wait(&s_full[g], j & 1);
+        const bool full_block = (valid == 128);
+        mbar_wait(&s_full[g], cnt & 1);
         tc_fence_after();
+        // whole S row -> registers, then hand the TMEM buffer straight back to the MMA warp
+        uint32_t sreg[128];
+        if (warp_live) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < nchunks) tmem_ld_32x32b_x32_p(t_s + c * 32, sreg + c * 32);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(&s_free[g]);
+
         float alpha = 1.f;
         float m_new = m_run;
         if (warp_live) {
-          // pass 1: row max
-          float mx = -INFINITY;
-          for (int c = 0; c < nchunks; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_s + c * 32, v);
-            tmem_ld_wait();
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          if (full_block) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int i = 0; i < 128; i += 2) {
+              mx0 = fmaxf(mx0, __uint_as_float(sreg[i]));
+              mx1 = fmaxf(mx1, __uint_as_float(sreg[i + 1]));
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c < nchunks) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (c * 32 + i < valid) mx0 = fmaxf(mx0, __uint_as_float(sreg[c * 32 + i]));
+              }
+            }
           }
-          m_new = fmaxf(m_run, mx * p.scale_log2);
+          m_new = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
           alpha = fast_exp2(m_run - m_new);
+          // exponentiate in registers first (sreg[i/2] <- packed bf16 pair), so that the wait for the
+          // previous block's P V (which still reads the P tile and writes O) comes as late as possible
+          l_run *= alpha;
+          float sum0 = 0.f, sum1 = 0.f;
+          const float neg_m = -m_new;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < nchunks) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const int idx = c * 32 + i;
+                float x0, x1;
+                ffma2(x0, x1, __uint_as_float(sreg[idx]), __uint_as_float(sreg[idx + 1]), p.scale_log2,
+                      p.scale_log2, neg_m, neg_m);
+                float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+                if (!full_block) {
+                  if (idx >= valid) e0 = 0.f;
+                  if (idx + 1 >= valid) e1 = 0.f;
+                }
+                fadd2(sum0, sum1, sum0, sum1, e0, e1);
+                sreg[idx >> 1] = pack_bf16x2(e0, e1);
+              }
+            }
+          }
+          l_run += sum0 + sum1;
+          m_run = m_new;
         }
         if (j > 0) {
-          mbar_wait(&o_full[g], (j - 1) & 1);  // P_g and O_g are free again
+          mbar_wait(&o_full[g], (cnt - 1) & 1);  // P_g and O_g are free again
           tc_fence_after();
           if (warp_live && __any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll
@@ -239,33 +322,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
         if (warp_live) {
-          l_run *= alpha;
-          float sum = 0.f;
-          for (int c = 0; c < nchunks; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_s + c * 32, v);
-            tmem_ld_wait();
-            float e[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-              e[i] = (c * 32 + i < valid) ? x : 0.f;
-              sum += e[i];
-            }
-            uint8_t* dst = p_row + (c >> 1) * 16384;
+          for (int c = 0; c < 4; ++c) {
+            if (c < nchunks) {
+              uint8_t* dst = p_row + (c >> 1) * 16384;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              uint4 pk;
-              pk.x = pack_bf16x2(e[t * 8 + 0], e[t * 8 + 1]);
-              pk.y = pack_bf16x2(e[t * 8 + 2], e[t * 8 + 3]);
-              pk.z = pack_bf16x2(e[t * 8 + 4], e[t * 8 + 5]);
-              pk.w = pack_bf16x2(e[t * 8 + 6], e[t * 8 + 7]);
-              const uint32_t c8 = static_cast<uint32_t>((c & 1) * 4 + t);
-              *reinterpret_cast<uint4*>(dst + ((c8 ^ sw) << 4)) = pk;
+              for (int t = 0; t < 4; ++t) {
+                const int w0 = c * 16 + t * 4;  // packed words of columns c*32 + t*8 .. +7
+                const uint32_t c8 = static_cast<uint32_t>((c & 1) * 4 + t);
+                *reinterpret_cast<uint4*>(dst + ((c8 ^ sw) << 4)) =
+                    make_uint4(sreg[w0], sreg[w0 + 1], sreg[w0 + 2], sreg[w0 + 3]);
+              }
             }
           }
-          l_run += sum;
-          m_run = m_new;
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -273,7 +342,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
 
       // epilogue: O / l -> bf16 -> global, one 2*HD-byte row per thread
-      mbar_wait(&o_full[g], (kvb - 1) & 1);
+      mbar_wait(&o_full[g], (cnt - 1) & 1);
       tc_fence_after();
       if (warp_live) {
         const float inv_l = 1.f / l_run;
@@ -304,6 +373,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qrow] =
               (m_run + log2f(l_run)) * 0.6931471805599453f;
       }
+      tc_fence_before();  // O_g reads retire before the next item's first P V overwrites it
     }
   }
 
@@ -350,8 +420,9 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const long long grid = (long long)p.B * p.H * p.q_pairs;
-  MB_REQUIRE(grid > 0 && grid < (1ll << 31), "mb_attn_fwd: grid %lld out of range", grid);
+  const long long items = (long long)p.B * p.H * p.q_pairs;
+  MB_REQUIRE(items > 0 && items < (1ll << 31), "mb_attn_fwd: %lld work items out of range", items);
+  const long long grid = items < sm_count() ? items : sm_count();  // persistent CTAs
   kern<<<(unsigned)grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   MB_CHECK_CUDA(cudaGetLastError());
   return 0;
