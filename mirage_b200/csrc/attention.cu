@@ -34,11 +34,22 @@ namespace mb200 {
 struct AttnDev {
   __nv_bfloat16* out;
   float* lse;
-  long long ldo;
+  const __nv_bfloat16* q;  // raw operands: CUDA-core tail paths only
+  const __nv_bfloat16* k;
+  const __nv_bfloat16* v;
+  long long ldq, ldk, ldv, ldo;
   int B, H, Nq, Nk;
+  // Rows / keys walked by the tensor-core tiles.  MIRAGE sequences are 128*t + 1 (the global token
+  // is appended LAST, mirage/model.py:390-391): the one-row / one-key remainder would cost a whole
+  // extra 128-row work item and an extra key block, so it is peeled off instead:
+  //   k_tail keys   -> rank-1 update on CUDA cores inside the softmax threads of this kernel
+  //   q_tail rows   -> attn_tail_rows_kernel (CUDA cores, one CTA per (batch, head))
+  int Nq_main, Nk_main, k_tail;
   int q_tiles, q_pairs, kv_blocks;
   float scale_log2;
 };
+
+constexpr int kMaxTail = 4;  // largest remainder (mod 128) that is peeled off instead of padded
 
 constexpr int kAttnThreads = 384;  // 3 warpgroups: {TMA, MMA, -, -}, softmax group 0, softmax group 1
 constexpr int kKvStages = 3;
@@ -174,7 +185,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (sc[g] > 0) mbar_wait(&s_free[g], (sc[g] - 1) & 1);
           if (g == 0) mbar_wait(&k_full[kc % kKvStages], (kc / kKvStages) & 1);
           tc_fence_after();
-          const int valid = min(128, p.Nk - j * 128);
+          const int valid = min(128, p.Nk_main - j * 128);
           const uint32_t idesc_s = make_idesc(128, static_cast<uint32_t>((valid + 15) & ~15), kFmtBF16, 0, 0);
           const uint32_t qa = q_addr + g * Cfg::kTileBytes;
           const uint32_t ka = k_addr + (kc % kKvStages) * Cfg::kTileBytes;
@@ -194,7 +205,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(&p_full[g], pc[g] & 1);
           if (g == 0) mbar_wait(&v_full[kc % kKvStages], (kc / kKvStages) & 1);
           tc_fence_after();
-          const int valid = min(128, p.Nk - j * 128);
+          const int valid = min(128, p.Nk_main - j * 128);
           const int ksteps = (valid + 15) >> 4;
           const uint32_t pa = p_addr + g * Cfg::kPBytes;
           const uint32_t va = v_addr + (kc % kKvStages) * Cfg::kTileBytes;
@@ -228,19 +239,58 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint8_t* p_row = smem + Cfg::kOffP + g * Cfg::kPBytes + r * 128;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     int cnt = 0;  // running count of key blocks this group has processed (barrier phases)
+    int item_i = 0;
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i) {
       const int pair = item % p.q_pairs;
       const int bh = item / p.q_pairs;
       const int h = bh % p.H, b = bh / p.H;
       if (pair * 2 + g >= p.q_tiles) continue;            // this group has no tile in the item
       const int qrow = (pair * 2 + g) * 128 + r;          // query index inside this (b, h)
-      const bool warp_live = (pair * 2 + g) * 128 + quarter * 32 < p.Nq;
+      const bool warp_live = (pair * 2 + g) * 128 + quarter * 32 < p.Nq_main;
       float m_run = -INFINITY;
       float l_run = 0.f;
 
+      // Peeled key tail (HD == 64 only, host-guaranteed kv_blocks >= 2 so the Q tile outlives this
+      // read): s_tail[t] = <q_row, k_tail_t> on CUDA cores, q from the swizzled smem tile, k broadcast
+      // from global.  The scores join the LAST key block's max / sum; P_tail V_tail is added to O in
+      // the epilogue.
+      float s_tail[kMaxTail];
+#pragma unroll
+      for (int t = 0; t < kMaxTail; ++t) s_tail[t] = -INFINITY;
+      if constexpr (HD == 64) {
+        if (p.k_tail > 0) {
+          mbar_wait(q_full, item_i & 1);
+          const uint32_t q_row_addr = smem_u32(smem + Cfg::kOffQ + g * Cfg::kTileBytes + r * 128);
+#pragma unroll
+          for (int t = 0; t < kMaxTail; ++t) {
+            if (t >= p.k_tail) break;
+            const uint4* krow = reinterpret_cast<const uint4*>(
+                p.k + (static_cast<long long>(b) * p.Nk + p.Nk_main + t) * p.ldk + h * HD);
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 qv = lds128(q_row_addr + ((static_cast<uint32_t>(c) ^ sw) << 4));
+              const uint4 kv4 = __ldg(krow + c);
+              const float2 q0 = unpack_bf16x2(__float_as_uint(qv.x)), k0 = unpack_bf16x2(kv4.x);
+              const float2 q1 = unpack_bf16x2(__float_as_uint(qv.y)), k1 = unpack_bf16x2(kv4.y);
+              const float2 q2 = unpack_bf16x2(__float_as_uint(qv.z)), k2 = unpack_bf16x2(kv4.z);
+              const float2 q3 = unpack_bf16x2(__float_as_uint(qv.w)), k3 = unpack_bf16x2(kv4.w);
+              acc0 = fmaf(q0.x, k0.x, acc0); acc1 = fmaf(q0.y, k0.y, acc1);
+              acc0 = fmaf(q1.x, k1.x, acc0); acc1 = fmaf(q1.y, k1.y, acc1);
+              acc0 = fmaf(q2.x, k2.x, acc0); acc1 = fmaf(q2.y, k2.y, acc1);
+              acc0 = fmaf(q3.x, k3.x, acc0); acc1 = fmaf(q3.y, k3.y, acc1);
+            }
+            s_tail[t] = acc0 + acc1;
+          }
+        }
+      }
+      float e_tail[kMaxTail];
+#pragma unroll
+      for (int t = 0; t < kMaxTail; ++t) e_tail[t] = 0.f;
+
       for (int j = 0; j < kvb; ++j, ++cnt) {
-        const int valid = min(128, p.Nk - j * 128);
+        const int valid = min(128, p.Nk_main - j * 128);
         const int nchunks = (valid + 31) >> 5;
         const bool full_block = (valid == 128);
         mbar_wait(&s_full[g], cnt & 1);
@@ -276,6 +326,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               }
             }
           }
+          if (HD == 64 && j == kvb - 1) {
+#pragma unroll
+            for (int t = 0; t < kMaxTail; ++t) mx0 = fmaxf(mx0, s_tail[t]);  // -inf when unused
+          }
           m_new = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
           alpha = fast_exp2(m_run - m_new);
           // exponentiate in registers first (sreg[i/2] <- packed bf16 pair), so that the wait for the
@@ -300,6 +354,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 fadd2(sum0, sum1, sum0, sum1, e0, e1);
                 sreg[idx >> 1] = pack_bf16x2(e0, e1);
               }
+            }
+          }
+          if (HD == 64 && j == kvb - 1) {
+#pragma unroll
+            for (int t = 0; t < kMaxTail; ++t) {
+              e_tail[t] = fast_exp2(fmaf(s_tail[t], p.scale_log2, neg_m));  // exp2(-inf) = 0
+              sum0 += e_tail[t];
             }
           }
           l_run += sum0 + sum1;
@@ -353,7 +414,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_o + c * 32, v);
           tmem_ld_wait();
-          if (qrow < p.Nq) {
+          if constexpr (HD == 64) {
+#pragma unroll
+            for (int t = 0; t < kMaxTail; ++t) {  // O += p_tail * v_tail (peeled keys)
+              if (t >= p.k_tail) break;
+              const uint4* vrow = reinterpret_cast<const uint4*>(
+                  p.v + (static_cast<long long>(b) * p.Nk + p.Nk_main + t) * p.ldv + h * HD + c * 32);
+              const float e = e_tail[t];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint4 vv = __ldg(vrow + u);
+                const float2 a0 = unpack_bf16x2(vv.x), a1 = unpack_bf16x2(vv.y),
+                             a2 = unpack_bf16x2(vv.z), a3 = unpack_bf16x2(vv.w);
+                v[u * 8 + 0] = __float_as_uint(fmaf(e, a0.x, __uint_as_float(v[u * 8 + 0])));
+                v[u * 8 + 1] = __float_as_uint(fmaf(e, a0.y, __uint_as_float(v[u * 8 + 1])));
+                v[u * 8 + 2] = __float_as_uint(fmaf(e, a1.x, __uint_as_float(v[u * 8 + 2])));
+                v[u * 8 + 3] = __float_as_uint(fmaf(e, a1.y, __uint_as_float(v[u * 8 + 3])));
+                v[u * 8 + 4] = __float_as_uint(fmaf(e, a2.x, __uint_as_float(v[u * 8 + 4])));
+                v[u * 8 + 5] = __float_as_uint(fmaf(e, a2.y, __uint_as_float(v[u * 8 + 5])));
+                v[u * 8 + 6] = __float_as_uint(fmaf(e, a3.x, __uint_as_float(v[u * 8 + 6])));
+                v[u * 8 + 7] = __float_as_uint(fmaf(e, a3.y, __uint_as_float(v[u * 8 + 7])));
+              }
+            }
+          }
+          if (qrow < p.Nq_main) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               uint4 pk;
@@ -369,7 +453,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
           }
         }
-        if (p.lse != nullptr && qrow < p.Nq)
+        if (p.lse != nullptr && qrow < p.Nq_main)
           p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qrow] =
               (m_run + log2f(l_run)) * 0.6931471805599453f;
       }
@@ -381,6 +465,92 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Peeled query rows [Nq_main, Nq) -- in MIRAGE the global token's query -- on CUDA cores.
+// One CTA per (batch, head); K and V of that head are streamed once from L2/HBM (128-byte rows),
+// so the kernel is bandwidth-bound: 2 * Nk * HD * 2 bytes per CTA.
+//   phase 1  thread t scores keys t, t+128, ...: s = <q, k> * scale*log2(e)        (K rows: 8 x 16 B)
+//   phase 2  block max / sum of exp2
+//   phase 3  warp w accumulates keys w, w+4, ... for the dim pair (2*lane, 2*lane+1) (V rows coalesced)
+// ---------------------------------------------------------------------------------------------
+constexpr int kTailThreads = 128;
+constexpr int kTailMaxKeys = 2048;
+
+template <int HD>
+__global__ void __launch_bounds__(kTailThreads)
+attn_tail_rows_kernel(const AttnDev p) {
+  static_assert(HD == 64, "tail rows are only peeled for head_dim 64");
+  __shared__ float s_p[kTailMaxKeys];
+  __shared__ float s_q[HD];
+  __shared__ float s_red[8];
+  __shared__ float s_o[4][HD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
+  const __nv_bfloat16* kbase = p.k + static_cast<long long>(b) * p.Nk * p.ldk + h * HD;
+  const __nv_bfloat16* vbase = p.v + static_cast<long long>(b) * p.Nk * p.ldv + h * HD;
+
+  for (int qrow = p.Nq_main; qrow < p.Nq; ++qrow) {
+    __syncthreads();
+    if (tid < HD)
+      s_q[tid] = __bfloat162float(p.q[(static_cast<long long>(b) * p.Nq + qrow) * p.ldq + h * HD + tid]) *
+                 p.scale_log2;
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int key = tid; key < p.Nk; key += kTailThreads) {
+      const uint4* krow = reinterpret_cast<const uint4*>(kbase + static_cast<long long>(key) * p.ldk);
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        const uint4 kv4 = __ldg(krow + c);
+        const float2 k0 = unpack_bf16x2(kv4.x), k1 = unpack_bf16x2(kv4.y), k2 = unpack_bf16x2(kv4.z),
+                     k3 = unpack_bf16x2(kv4.w);
+        acc0 = fmaf(s_q[c * 8 + 0], k0.x, acc0); acc1 = fmaf(s_q[c * 8 + 1], k0.y, acc1);
+        acc0 = fmaf(s_q[c * 8 + 2], k1.x, acc0); acc1 = fmaf(s_q[c * 8 + 3], k1.y, acc1);
+        acc0 = fmaf(s_q[c * 8 + 4], k2.x, acc0); acc1 = fmaf(s_q[c * 8 + 5], k2.y, acc1);
+        acc0 = fmaf(s_q[c * 8 + 6], k3.x, acc0); acc1 = fmaf(s_q[c * 8 + 7], k3.y, acc1);
+      }
+      const float sc = acc0 + acc1;
+      s_p[key] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    float sum = 0.f;
+    for (int key = tid; key < p.Nk; key += kTailThreads) {
+      const float e = fast_exp2(s_p[key] - mx);
+      s_p[key] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[4 + warp] = sum;
+    __syncthreads();
+    sum = s_red[4] + s_red[5] + s_red[6] + s_red[7];
+    // P V: warp w takes keys w, w+4, ...; lane owns dims 2*lane, 2*lane+1
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll 8
+    for (int key = warp; key < p.Nk; key += 4) {
+      const uint32_t vv =
+          __ldg(reinterpret_cast<const uint32_t*>(vbase + static_cast<long long>(key) * p.ldv) + lane);
+      const float2 vf = unpack_bf16x2(vv);
+      const float e = s_p[key];
+      o0 = fmaf(e, vf.x, o0);
+      o1 = fmaf(e, vf.y, o1);
+    }
+    s_o[warp][2 * lane] = o0;
+    s_o[warp][2 * lane + 1] = o1;
+    __syncthreads();
+    if (tid < HD) {
+      const float o = (s_o[0][tid] + s_o[1][tid] + s_o[2][tid] + s_o[3][tid]) / sum;
+      p.out[(static_cast<long long>(b) * p.Nq + qrow) * p.ldo + h * HD + tid] = __float2bfloat16(o);
+    }
+    if (tid == 0 && p.lse != nullptr)
+      p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qrow] = (mx + log2f(sum)) * 0.6931471805599453f;
+  }
 }
 
 template <int HD>
@@ -404,14 +574,30 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
   AttnDev p;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.lse = a->lse;
+  p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
+  p.k = reinterpret_cast<const __nv_bfloat16*>(a->k);
+  p.v = reinterpret_cast<const __nv_bfloat16*>(a->v);
+  p.ldq = a->ldq;
+  p.ldk = a->ldk;
+  p.ldv = a->ldv;
   p.ldo = a->ldo;
   p.B = (int)a->batch;
   p.H = (int)a->heads;
   p.Nq = (int)a->nq;
   p.Nk = (int)a->nk;
-  p.q_tiles = (p.Nq + 127) / 128;
+  // peel a 1..kMaxTail remainder off the key / query ranges (see AttnDev)
+  p.Nk_main = p.Nk;
+  p.k_tail = 0;
+  if (HD == 64 && p.Nk >= 256 && p.Nk % 128 >= 1 && p.Nk % 128 <= kMaxTail) {
+    p.k_tail = p.Nk % 128;
+    p.Nk_main = p.Nk - p.k_tail;
+  }
+  p.Nq_main = p.Nq;
+  if (HD == 64 && p.Nq >= 128 && p.Nq % 128 >= 1 && p.Nq % 128 <= kMaxTail && p.Nk <= kTailMaxKeys)
+    p.Nq_main = p.Nq - p.Nq % 128;
+  p.q_tiles = (p.Nq_main + 127) / 128;
   p.q_pairs = (p.q_tiles + 1) / 2;
-  p.kv_blocks = (p.Nk + 127) / 128;
+  p.kv_blocks = (p.Nk_main + 127) / 128;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   auto kern = attn_fwd_kernel<HD>;
   static bool configured = false;
@@ -425,6 +611,11 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
   const long long grid = items < sm_count() ? items : sm_count();  // persistent CTAs
   kern<<<(unsigned)grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   MB_CHECK_CUDA(cudaGetLastError());
+  if constexpr (HD == 64) {
+    if (p.Nq_main < p.Nq)
+      attn_tail_rows_kernel<HD><<<(unsigned)(p.B * p.H), kTailThreads, 0, stream>>>(p);
+    MB_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

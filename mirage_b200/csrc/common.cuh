@@ -515,6 +515,62 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f));
 }
 
+// Forward GELU for the GEMM epilogue, one MUFU + 7 FMA-pipe slots per element (the A&S form above
+// needs two MUFUs and ~16 slots, which made the fc1 epilogue, not the tensor pipe, the bound of
+// that GEMM: ncu r01, 1442 us vs 790 us for the same tile loop with a plain bf16 epilogue).
+//   erf-GELU(x) = 0.5 x (1 + erf(x / sqrt 2))  ~=  0.5 x (1 + tanh(x (a + b x^2 + c x^4)))
+// a, b, c: least-squares fit to the exact erf form on [-8, 8], max |error| 3.0e-5 (oracle/fit_gelu.py);
+// x^2 is clamped at 64 so the quartic never turns over (tanh is saturated there: 13.6).
+// tanh.approx.f32 adds <= 2^-11 relative error in t, i.e. <= 2.5e-4 |x| absolute -- an order of
+// magnitude below the bf16 rounding of the stored activation.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float x2 = fminf(x * x, 64.0f);
+  float p = fmaf(-3.58732362e-04f, x2, 3.70503451e-02f);
+  p = fmaf(p, x2, 7.97458471e-01f);
+  const float t = tanh_approx(x * p);
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+
+// two elements at once on the packed fp32x2 FMA pipe (Blackwell FMUL2 / FFMA2)
+__device__ __forceinline__ void gelu_fast2(float& a, float& b) {
+  float ta, tb;
+  asm("{\n"
+      ".reg .b64 x, x2, p, c2, c1, c0, hh, h, t;\n"
+      ".reg .f32 lo, hi;\n"
+      "mov.b64 x, {%2, %3};\n"
+      "mul.rn.f32x2 x2, x, x;\n"
+      "mov.b64 {lo, hi}, x2;\n"
+      "min.f32 lo, lo, 0f42800000;\n"
+      "min.f32 hi, hi, 0f42800000;\n"
+      "mov.b64 x2, {lo, hi};\n"
+      "mov.b64 c2, {0fB9BC143E, 0fB9BC143E};\n"   // -3.58732362e-04
+      "mov.b64 c1, {0f3D17C21A, 0f3D17C21A};\n"   //  3.70503451e-02
+      "mov.b64 c0, {0f3F4C263D, 0f3F4C263D};\n"   //  7.97458471e-01
+      "mov.b64 hh, {0f3F000000, 0f3F000000};\n"   //  0.5
+      "fma.rn.f32x2 p, c2, x2, c1;\n"
+      "fma.rn.f32x2 p, p, x2, c0;\n"
+      "mul.rn.f32x2 p, p, x;\n"
+      "mov.b64 {lo, hi}, p;\n"
+      "tanh.approx.f32 lo, lo;\n"
+      "tanh.approx.f32 hi, hi;\n"
+      "mov.b64 t, {lo, hi};\n"
+      "mul.rn.f32x2 h, x, hh;\n"
+      "fma.rn.f32x2 t, h, t, h;\n"
+      "mov.b64 {%0, %1}, t;\n"
+      "}\n"
+      : "=f"(ta), "=f"(tb)
+      : "f"(a), "f"(b));
+  a = ta;
+  b = tb;
+}
+
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f));
   float e;

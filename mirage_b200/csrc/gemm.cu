@@ -27,9 +27,10 @@ int dispatch_gemm_pair(int bn, int layout, int epi, const CUtensorMap& ta, const
   return rc;
 }
 
-// Estimated time ~ waves * BN * penalty.  Pair tiles (256 rows) halve the B traffic per SM; the 1-CTA
-// kernel is L2-operand-bound at BN=128 and shared-memory-bound at BN=64, but offers twice as many,
-// smaller tiles for problems that cannot fill 74 CTA pairs.
+// Estimated time ~ waves * BN * penalty: every SM owns 128 output rows of a tile in both kernels (a
+// pair tile is 256 rows over 2 SMs), so the per-SM work of one wave is proportional to BN.  Pair tiles
+// halve the B traffic per SM; the 1-CTA kernel is L2-operand-bound at BN=128 and shared-memory-bound at
+// BN=64, but offers twice as many, smaller tiles for problems that cannot fill 74 CTA pairs.
 static void pick_tiling(long long m, long long n, int splits, int force_bn, int force_pair, bool pair_ok,
                         int* bn_out, bool* pair_out) {
   const int sms = sm_count();
@@ -47,7 +48,7 @@ static void pick_tiling(long long m, long long n, int splits, int force_bn, int 
     const long long tiles = ((m + bm - 1) / bm) * ((n + c.bn - 1) / c.bn) * splits;
     const long long slots = c.pair ? sms / 2 : sms;
     const long long waves = (tiles + slots - 1) / slots;
-    const double cost = double(waves) * c.bn * c.penalty * (c.pair ? 1.0 : 0.5) * 2.0;
+    const double cost = double(waves) * c.bn * c.penalty;
     if (cost < best) {
       best = cost;
       *bn_out = c.bn;

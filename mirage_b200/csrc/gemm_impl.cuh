@@ -148,7 +148,7 @@ static __device__ __noinline__ void epi_generic_chunk(const GemmDev& p, float4 a
       pk.y = pack_bf16x2(f2, f3);
       *reinterpret_cast<uint2*>(p.aux_out + (long long)row * p.ld_aux + col) = pk;
     }
-    f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3);
+    gelu_fast2(f0, f1); gelu_fast2(f2, f3);
   }
   if (p.epilogue & MB_EPI_DGELU) {
     const uint2 pk = __ldg(reinterpret_cast<const uint2*>(p.aux_in + (long long)row * p.ld_aux + col));
@@ -272,7 +272,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
             pk.y = pack_bf16x2(f2, f3);
             *reinterpret_cast<uint2*>(aptr + it * astep) = pk;
           }
-          f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3);
+          gelu_fast2(f0, f1); gelu_fast2(f2, f3);
         }
         if constexpr (MODE == EPI_DGELU) {
           const float2 h0 = unpack_bf16x2(cur.aux[it].x), h1 = unpack_bf16x2(cur.aux[it].y);

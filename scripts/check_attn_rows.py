@@ -62,6 +62,13 @@ def group_attn64():
     ok &= attn_case(3, 16, 257, 257, 64)
     ok &= attn_case(2, 4, 1025, 1025, 64)
     ok &= attn_case(2, 4, 200, 77, 64, self_attn=False)
+    # peeled remainders (global tokens appended last): key tail inside the tile kernel, query tail rows
+    ok &= attn_case(2, 4, 258, 258, 64)                    # 2 global tokens
+    ok &= attn_case(1, 3, 772, 772, 64)                    # 3 modalities + 4 global tokens
+    ok &= attn_case(2, 2, 256, 513, 64, self_attn=False)   # key tail only
+    ok &= attn_case(2, 2, 513, 256, 64, self_attn=False)   # query tail only
+    ok &= attn_case(2, 2, 129, 129, 64)                    # query tail peeled, keys padded (nk < 256)
+    ok &= attn_case(2, 2, 133, 261, 64, self_attn=False)   # remainder 5: nothing peeled
     return ok
 
 

@@ -232,6 +232,42 @@ def group_perf():
     return True
 
 
+def _time(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def group_perfepi():
+    """Epilogue variants of the encoder's GEMMs at cfg-2 size (the tile loop is identical; only the
+    epilogue differs), against the plain bf16 store."""
+    m = 131328
+    for (n, k, what) in [(4096, 1024, "gelu"), (4096, 1024, "gelu+aux"), (1024, 4096, "res"), (1024, 1024, "res"),
+                         (3072, 1024, "bf16")]:
+        a, w = mk(m, k), mk(n, k, scale=k ** -0.5)
+        bias = torch.randn(n, device=dev)
+        if what == "res":
+            x = torch.randn(m, n, device=dev)
+            fn = lambda: ops.gemm(a, w, m=m, n=n, k=k, bias=bias, residual=x, out=x)
+        elif what.startswith("gelu"):
+            out = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+            pre = torch.empty(m, n, dtype=torch.bfloat16, device=dev) if what == "gelu+aux" else None
+            fn = lambda: ops.gemm(a, w, m=m, n=n, k=k, bias=bias, gelu=True, aux_out=pre, out=out)
+        else:
+            out = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+            fn = lambda: ops.gemm(a, w, m=m, n=n, k=k, bias=bias, out=out)
+        ms = _time(fn)
+        print(f"[PERF] {what:9s} m={m} n={n} k={k}: {ms:.3f} ms = {2.0 * m * n * k / ms / 1e9:.0f} TFLOP/s", flush=True)
+    return True
+
+
 if __name__ == "__main__":
     grp = sys.argv[1]
     t0 = time.time()
