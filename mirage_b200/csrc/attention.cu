@@ -6,27 +6,32 @@
 //   mirage/utils.py:181-185 (Attention)  and  mirage/utils.py:216-220 (CrossAttention).
 //
 // Persistent CTAs (one per SM) walk work items = (batch, head, pair of 128-row query tiles); within an
-// item the keys are walked in blocks of 128 (the last block is shortened to a multiple of 16 keys).
-// The TMA producer and the MMA warp run ahead into the next item while the softmax warps finish the
-// current one, so there is no per-item pipeline fill bubble.
+// item the keys are walked in blocks of 128 (a ragged last block is shortened to a multiple of 16).
+// Every role runs ahead across item boundaries (Q is double-buffered), so there is no per-item
+// pipeline fill or drain on the softmax warps:
 //
-//   warp 0      TMA producer: Q tiles once, then K_j / V_j through a 3-stage ring
-//   warp 1      TMEM allocator + MMA issuer (one lane; warps 2-3 idle; the whole warpgroup gives its
-//               registers to the softmax warps with setmaxnreg):
-//                   S_g = Q_g K_j^T      (SS, both K-major,      accumulator S_g in TMEM)
-//                   O_g += P_g V_j       (SS, P K-major from smem, V MN-major, accumulator O_g)
-//   warps 4-7   softmax group 0 (one thread per query row, no shuffles, 224 registers)
-//   warps 8-11  softmax group 1
+//   warp 0       TMA producer: Q tiles (+ the peeled key/value tail rows) per item, K_j / V_j through
+//                3-stage rings
+//   warp 1       TMEM allocator + MMA issuer (one lane), S always one block ahead of P V:
+//                    S_g = Q_g K_j^T      (SS: both operands K-major in smem, accumulator S_g in TMEM)
+//                    O_g += P_g V_j       (TS: P_g read from TMEM as the A operand, V MN-major in smem)
+//   warps 4-7    softmax group 0, one thread per query row, no shuffles (208 registers)
+//   warps 8-11   softmax group 1
+//   warps 12-15  epilogue: O_g / l -> bf16 -> global (+ LSE) once the item's last P V retired, so the
+//                softmax warps never wait for the drain of their own accumulator
 //
 // Each softmax thread pulls its whole S row (128 fp32) into registers with one round of tcgen05.ld and
-// releases the TMEM buffer at once (s_free), so the MMA warp can already run S_g(j+1) while the row is
-// being exponentiated; the MMA warp is an event-driven scheduler polling {s_free, p_full} of both
-// groups, so neither group ever waits for the other.  Softmax runs in the log2 domain with a running
-// max m and sum l per row (packed FFMA2/FADD2, masking only in the ragged last key block); O is
-// rescaled in TMEM (tcgen05.ld / st) only when some row max in the warp actually moved.
+// releases the S buffer at once (s_free): S_g(j+1) runs while the row is being exponentiated.  The
+// exponentials are packed to bf16 in registers and written back to TMEM (P_g) with tcgen05.st -- no
+// shared-memory round trip, no proxy fence.  Softmax runs in the log2 domain with a running max m and
+// sum l per row (packed FFMA2 / FADD2).  The max is LAZY: m only moves (and O is only rescaled in
+// TMEM) when some row of the warp grew by more than 2^8 -- P stays <= 256, well inside bf16/fp32
+// range, and the final O / l is unchanged -- so the TMEM read-modify-write of O is off the common path.
 //
-// TMEM columns: S_0 [0,128)  S_1 [128,256)  O_0 [256,256+HD)  O_1 [320,320+HD).
+// TMEM columns: S_0 [0,128)  S_1 [128,256)  O_0 [256,256+HD)  O_1 [320,320+HD)  P_0 [384,448)  P_1 [448,512).
 #include "../../include/mirage_b200.h"
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mb200 {
@@ -42,33 +47,173 @@ struct AttnDev {
   // Rows / keys walked by the tensor-core tiles.  MIRAGE sequences are 128*t + 1 (the global token
   // is appended LAST, mirage/model.py:390-391): the one-row / one-key remainder would cost a whole
   // extra 128-row work item and an extra key block, so it is peeled off instead:
-  //   k_tail keys   -> rank-1 update on CUDA cores inside the softmax threads of this kernel
+  //   k_tail keys   -> rank-1 update on CUDA cores (scores in the softmax threads, P_tail V_tail in
+  //                    the epilogue warps); the rows travel to smem with the item's Q tiles
   //   q_tail rows   -> attn_tail_rows_kernel (CUDA cores, one CTA per (batch, head))
   int Nq_main, Nk_main, k_tail;
   int q_tiles, q_pairs, kv_blocks;
+  int stagger;  // cycles softmax group 1 idles once at kernel start (anti-phases the two groups)
   float scale_log2;
 };
 
 constexpr int kMaxTail = 4;  // largest remainder (mod 128) that is peeled off instead of padded
 
-constexpr int kAttnThreads = 384;  // 3 warpgroups: {TMA, MMA, -, -}, softmax group 0, softmax group 1
+constexpr int kAttnThreads = 512;  // 4 warpgroups: {TMA, MMA, -, -}, softmax 0, softmax 1, epilogue
 constexpr int kKvStages = 3;
+constexpr int kDefaultPoly = 0;
+constexpr int kDefaultStagger = 0;
+constexpr float kLazyMaxLog2 = 8.0f;  // rescale O only when a row max grew by more than 2^8
 
 template <int HD>
 struct AttnCfg {
-  static constexpr int kRowBytes = HD * 2;          // 128 (SW128) or 64 (SW64)
+  static constexpr int kRowBytes = HD * 2;            // 128 (SW128) or 64 (SW64)
   static constexpr int kTileBytes = 128 * kRowBytes;  // Q / K / V tile of 128 rows
-  static constexpr int kPBytes = 128 * 128 * 2;     // P tile: 128 rows x 128 keys, bf16
-  static constexpr int kOffQ = 0;
-  static constexpr int kOffK = kOffQ + 2 * kTileBytes;
+  static constexpr int kOffQ = 0;                     // 2 item slots x 2 tiles
+  static constexpr int kOffK = kOffQ + 4 * kTileBytes;
   static constexpr int kOffV = kOffK + kKvStages * kTileBytes;
-  static constexpr int kOffP = kOffV + kKvStages * kTileBytes;
-  static constexpr int kOffBar = kOffP + 2 * kPBytes;
-  static constexpr int kSmemBytes = kOffBar + 256;
+  static constexpr int kOffTail = kOffV + kKvStages * kTileBytes;  // 2 slots x {k rows, v rows}
+  static constexpr int kTailSlotBytes = 2 * kMaxTail * 128;
+  static constexpr int kOffStats = kOffTail + 2 * kTailSlotBytes;  // [parity][group][field][row] f32
+  static constexpr int kStatFields = 2 + kMaxTail;                 // 1/l, lse, e_tail[]
+  static constexpr int kStatsBytes = 2 * 2 * kStatFields * 128 * 4;
+  static constexpr int kOffBar = kOffStats + kStatsBytes;
+  static constexpr int kSmemBytes = kOffBar + 512;
   static constexpr int kSwizzle = (HD == 64) ? 128 : 64;
 };
 
-template <int HD>
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (P, bf16 pairs, one query row per TMEM lane) is read
+// from tensor memory; issued by ONE thread.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// plain (non-tensor) bulk copy global -> smem, completion bytes credited to an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                          uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// 2^x for a pair of elements on the FMA pipe instead of the MUFU (the softmax is bound by the 16
+// ex2/clk/SM of the XU pipe: ncu r01 v4, mio/XU throttle on every MUFU.EX2).  Cody-Waite: n = rint(x)
+// through the 1.5*2^23 magic constant, f = x - n in [-0.5, 0.5], 2^f by a cubic (max rel. error 2.1e-4,
+// an order of magnitude below the bf16 rounding of P), exponent patched in with one integer IMAD.
+__device__ __forceinline__ void exp2_poly2(float& e0, float& e1, float x0, float x1) {
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23
+  float t0, t1, n0, n1, f0, f1, p0, p1;
+  fadd2(t0, t1, x0, x1, kMagic, kMagic);
+  fadd2(n0, n1, t0, t1, -kMagic, -kMagic);
+  ffma2(f0, f1, n0, n1, -1.f, -1.f, x0, x1);
+  ffma2(p0, p1, f0, f1, 0.054850947f, 0.054850947f, 0.24181366f, 0.24181366f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.69324836f, 0.69324836f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.99998821f, 0.99998821f);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// order-pinned (asm volatile) forms for exp_row's three passes
+__device__ __forceinline__ void ffma2_v(uint32_t& d0, uint32_t& d1, float b, float c) {
+  asm volatile(
+      "{\n"
+      ".reg .b64 ra, rb, rc;\n"
+      "mov.b64 ra, {%0, %1};\n"
+      "mov.b64 rb, {%2, %2};\n"
+      "mov.b64 rc, {%3, %3};\n"
+      "fma.rn.f32x2 ra, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, ra;\n"
+      "}\n"
+      : "+r"(d0), "+r"(d1)
+      : "f"(b), "f"(c));
+}
+
+__device__ __forceinline__ void ex2_v(uint32_t& x) {
+  asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(x));
+}
+
+__device__ __forceinline__ void fadd2_v(float& s0, float& s1, uint32_t a0, uint32_t a1) {
+  asm volatile(
+      "{\n"
+      ".reg .b64 ra, rs;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rs, {%0, %1};\n"
+      "add.rn.f32x2 rs, rs, ra;\n"
+      "mov.b64 {%0, %1}, rs;\n"
+      "}\n"
+      : "+f"(s0), "+f"(s1)
+      : "r"(a0), "r"(a1));
+}
+
+// exponentiate one S row held in registers: sreg[i] (fp32 bits, i < 32*nchunks) -> packed bf16 pairs
+// in sreg[i/2]; returns the row sum.  FULL: all 128 columns valid, no masking code at all.
+// Three passes in pinned program order, each a run of mutually independent instructions (the
+// compiler's own interleaving left every instruction waiting on its predecessor: ncu r01 v4, 7 clk per
+// instruction with 'wait' the top stall):  x = s*scale - m (64 FFMA2);  e = 2^x in place (128 MUFU,
+// back to back -- the XU pipe is the only thing that should stall here, and the other softmax warp of
+// the SM sub-partition issues into the gaps);  row sum on 4 independent FADD2 chains + bf16 packing.
+// POLY: of every 16 element pairs, this many go through exp2_poly2 instead of MUFU.EX2.
+template <bool FULL, int POLY>
+__device__ __forceinline__ float exp_row(uint32_t (&sreg)[128], float scale_log2, float neg_m, int valid,
+                                         int nchunks) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (FULL || c < nchunks) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) ffma2_v(sreg[c * 32 + i], sreg[c * 32 + i + 1], scale_log2, neg_m);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (FULL || c < nchunks) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const int idx = c * 32 + i;
+        if (((i >> 1) * POLY) / 16 != (((i >> 1) + 1) * POLY) / 16) {
+          float e0, e1;
+          exp2_poly2(e0, e1, __uint_as_float(sreg[idx]), __uint_as_float(sreg[idx + 1]));
+          sreg[idx] = __float_as_uint(e0);
+          sreg[idx + 1] = __float_as_uint(e1);
+        } else {
+          ex2_v(sreg[idx]);
+          ex2_v(sreg[idx + 1]);
+        }
+        if (!FULL) {
+          if (idx >= valid) sreg[idx] = 0u;
+          if (idx + 1 >= valid) sreg[idx + 1] = 0u;
+        }
+      }
+    }
+  }
+  float sum[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) sum[a] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (FULL || c < nchunks) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const int idx = c * 32 + i;
+        const int a = (i >> 1) & 3;
+        fadd2_v(sum[2 * a], sum[2 * a + 1], sreg[idx], sreg[idx + 1]);
+        sreg[idx >> 1] = pack_bf16x2(__uint_as_float(sreg[idx]), __uint_as_float(sreg[idx + 1]));
+      }
+    }
+  }
+  return ((sum[0] + sum[1]) + (sum[2] + sum[3])) + ((sum[4] + sum[5]) + (sum[6] + sum[7]));
+}
+
+template <int HD, int POLY>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnDev p) {
@@ -78,17 +223,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
-  uint64_t* q_full = bars;                    // 1
-  uint64_t* k_full = bars + 1;                // 3
-  uint64_t* k_empty = bars + 4;               // 3
-  uint64_t* v_full = bars + 7;                // 3
-  uint64_t* v_empty = bars + 10;              // 3
-  uint64_t* s_full = bars + 13;               // 2
-  uint64_t* p_full = bars + 15;               // 2
-  uint64_t* o_full = bars + 17;               // 2
-  uint64_t* s_free = bars + 19;               // 2
-  uint64_t* q_empty = bars + 21;              // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* q_full = bars;                    // 2   TMA tx (Q tiles + tail rows of the item)
+  uint64_t* q_empty = bars + 2;               // 2   MMA commit after the item's last S
+  uint64_t* k_full = bars + 4;                // 3
+  uint64_t* k_empty = bars + 7;               // 3
+  uint64_t* v_full = bars + 10;               // 3
+  uint64_t* v_empty = bars + 13;              // 3
+  uint64_t* s_full = bars + 16;               // 2   MMA commit: S_g(j) complete
+  uint64_t* s_free = bars + 18;               // 2   128 softmax threads: S_g copied to registers
+  uint64_t* p_full = bars + 20;               // 2   128 softmax threads: P_g(j) in TMEM
+  uint64_t* o_full = bars + 22;               // 2   MMA commit: P_g V(j) retired
+  uint64_t* o_free = bars + 24;               // 2   4 epilogue warps: O_g of the item read out
+  uint64_t* stats_full = bars + 26;           // 2   128 softmax threads: row statistics of the item
+  uint64_t* tail_free = bars + 28;            // 2   4 epilogue warps: tail rows of the item slot consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  float* stats = reinterpret_cast<float*>(smem + Cfg::kOffStats);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,19 +254,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 2);  // one commit per MMA issuer
+      mbar_init(&tail_free[s], 4);
+    }
     for (int s = 0; s < kKvStages; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
+      mbar_init(&k_empty[s], 2);
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&v_empty[s], 2);
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
+      mbar_init(&s_free[g], 128);
       mbar_init(&p_full[g], 128);
       mbar_init(&o_full[g], 1);
-      mbar_init(&s_free[g], 128);
+      mbar_init(&o_free[g], 4);
+      mbar_init(&stats_full[g], 128);
     }
     mbar_fence_init();
   }
@@ -130,12 +284,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Persistent CTA: every role walks the same static list of work items; all barrier phases are
-  // tracked with running counters, so the producer / MMA warp run ahead into the next item while the
-  // softmax warps are still finishing the current one.
+  auto groups_of = [&](int item) { return ((item % p.q_pairs) * 2 + 1 < p.q_tiles) ? 2 : 1; };
+
+  // All barrier phases are tracked with running counters; every role walks the same static list of
+  // work items.
   if (warp < 4) {
-    // registers of this warpgroup go to the softmax warpgroups (a whole 128-wide S row lives there)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0 && lane == 0) {
       // -------------------------------------------------------------- TMA producer
       int kv_count = 0, item_i = 0;
@@ -143,139 +297,173 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int pair = item % p.q_pairs;
         const int bh = item / p.q_pairs;
         const int h = bh % p.H, b = bh / p.H;
-        const int n_groups = (pair * 2 + 1 < p.q_tiles) ? 2 : 1;
-        mbar_wait(q_empty, (item_i & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, n_groups * Cfg::kTileBytes);
+        const int n_groups = groups_of(item);
+        const int slot = item_i & 1;
+        const uint32_t ph = (item_i >> 1) & 1;
+        mbar_wait(&q_empty[slot], ph ^ 1);
+        uint32_t bytes = n_groups * Cfg::kTileBytes;
+        if (HD == 64 && p.k_tail > 0) {
+          mbar_wait(&tail_free[slot], ph ^ 1);
+          bytes += 2 * p.k_tail * 128;
+        }
+        mbar_arrive_expect_tx(&q_full[slot], bytes);
         for (int g = 0; g < n_groups; ++g)
-          tma_load_3d(smem + Cfg::kOffQ + g * Cfg::kTileBytes, &tm_q, q_full, h * HD,
+          tma_load_3d(smem + Cfg::kOffQ + (slot * 2 + g) * Cfg::kTileBytes, &tm_q, &q_full[slot], h * HD,
                       (pair * 2 + g) * 128, b);
+        if (HD == 64) {
+          uint8_t* tslot = smem + Cfg::kOffTail + slot * Cfg::kTailSlotBytes;
+          for (int t = 0; t < p.k_tail; ++t) {
+            const long long row = static_cast<long long>(b) * p.Nk + p.Nk_main + t;
+            bulk_load(tslot + t * 128, p.k + row * p.ldk + h * HD, 128, &q_full[slot]);
+            bulk_load(tslot + (kMaxTail + t) * 128, p.v + row * p.ldv + h * HD, 128, &q_full[slot]);
+          }
+        }
         for (int j = 0; j < kvb; ++j, ++kv_count) {
           const int s = kv_count % kKvStages;
-          const uint32_t ph = (kv_count / kKvStages) & 1;
-          mbar_wait(&k_empty[s], ph ^ 1);
+          const uint32_t kph = (kv_count / kKvStages) & 1;
+          mbar_wait(&k_empty[s], kph ^ 1);
           mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
           tma_load_3d(smem + Cfg::kOffK + s * Cfg::kTileBytes, &tm_k, &k_full[s], h * HD, j * 128, b);
-          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_wait(&v_empty[s], kph ^ 1);
           mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
           tma_load_3d(smem + Cfg::kOffV + s * Cfg::kTileBytes, &tm_v, &v_full[s], h * HD, j * 128, b);
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // -------------------------------------------------------------- MMA issuer
-      // One thread, blocking waits in the order the events occur when the two softmax groups
-      // ping-pong half a block apart:
-      //   S_0(0) S_1(0);  for j: { S_0(j+1), S_1(j+1)  (S buffer released: softmax holds the row in
-      //   registers);  P_0 V(j), P_1 V(j)  (P tile written) }
-      // (a polling scheduler over mbarrier.test_wait lost ~1000 clk per event to test_wait latency).
+    } else if ((warp == 1 || warp == 2) && lane == 0) {
+      // -------------------------------------------------------------- MMA issuers
+      // One issuing thread PER softmax group (warp 1 -> group 0, warp 2 -> group 1), each with blocking
+      // waits in its own group's event order: S_g(j+1), then P_g V(j).  S runs one key block ahead of
+      // P V -- also across item boundaries (the next item's Q sits in the other slot).  A single
+      // in-order issuer coupled the groups: a wait for one group's P delayed the other group's S and
+      // pulled both groups into lockstep, where they fight for the MUFU at the same time.
+      // The shared K / V / Q slots are released by two commits (one per issuer; the issuer of group 0
+      // commits twice for an item that has only one query tile).
+      const int g = warp - 1;
       const uint32_t q_addr = smem_u32(smem + Cfg::kOffQ);
       const uint32_t k_addr = smem_u32(smem + Cfg::kOffK);
       const uint32_t v_addr = smem_u32(smem + Cfg::kOffV);
-      const uint32_t p_addr = smem_u32(smem + Cfg::kOffP);
       constexpr uint32_t idesc_pv = make_idesc(128, HD, kFmtBF16, 0, 1);
-      int sc[2] = {0, 0};  // running count of S MMAs per group (phase of s_full / s_free)
-      int pc[2] = {0, 0};  // running count of PV MMAs per group (phase of p_full / o_full)
-      int kv_base = 0;     // running key-block counter at the start of the item (ring slot / phase)
-      int item_i = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i, kv_base += kvb) {
-        const int pair = item % p.q_pairs;
-        const int n_groups = (pair * 2 + 1 < p.q_tiles) ? 2 : 1;
+      int sc = 0;  // S MMAs issued        (phase of s_full / s_free)
+      int pc = 0;  // P V MMAs issued      (phase of p_full / o_full)
+      int oc = 0;  // items finished       (phase of o_free)
 
-        auto issue_s = [&](int g, int j) {
-          const int kc = kv_base + j;
-          if (sc[g] > 0) mbar_wait(&s_free[g], (sc[g] - 1) & 1);
-          if (g == 0) mbar_wait(&k_full[kc % kKvStages], (kc / kKvStages) & 1);
-          tc_fence_after();
-          const int valid = min(128, p.Nk_main - j * 128);
-          const uint32_t idesc_s = make_idesc(128, static_cast<uint32_t>((valid + 15) & ~15), kFmtBF16, 0, 0);
-          const uint32_t qa = q_addr + g * Cfg::kTileBytes;
-          const uint32_t ka = k_addr + (kc % kKvStages) * Cfg::kTileBytes;
+      auto issue_s = [&](int n_groups, int item_i, int j, int kc) {
+        if (sc > 0) mbar_wait(&s_free[g], (sc - 1) & 1);
+        mbar_wait(&k_full[kc % kKvStages], (kc / kKvStages) & 1);
+        tc_fence_after();
+        const int valid = min(128, p.Nk_main - j * 128);
+        const uint32_t idesc_s = make_idesc(128, static_cast<uint32_t>((valid + 15) & ~15), kFmtBF16, 0, 0);
+        const uint32_t qa = q_addr + ((item_i & 1) * 2 + g) * Cfg::kTileBytes;
+        const uint32_t ka = k_addr + (kc % kKvStages) * Cfg::kTileBytes;
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_f16_ss(tmem_base + g * 128, make_smem_desc(qa + k * 32, 0, kSbo, kSw),
-                        make_smem_desc(ka + k * 32, 0, kSbo, kSw), idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(&s_full[g]);
-          ++sc[g];
-          if (g == n_groups - 1) {
-            umma_commit(&k_empty[kc % kKvStages]);   // both groups' S(j) are issued
-            if (j == kvb - 1) umma_commit(q_empty);  // last S of the item: the Q tiles may go
-          }
-        };
-        auto issue_pv = [&](int g, int j) {
-          const int kc = kv_base + j;
-          mbar_wait(&p_full[g], pc[g] & 1);
-          if (g == 0) mbar_wait(&v_full[kc % kKvStages], (kc / kKvStages) & 1);
-          tc_fence_after();
-          const int valid = min(128, p.Nk_main - j * 128);
-          const int ksteps = (valid + 15) >> 4;
-          const uint32_t pa = p_addr + g * Cfg::kPBytes;
-          const uint32_t va = v_addr + (kc % kKvStages) * Cfg::kTileBytes;
-          for (int kk = 0; kk < ksteps; ++kk)
-            umma_f16_ss(tmem_base + 256 + g * 64,
-                        make_smem_desc(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
-                        make_smem_desc(va + kk * 16 * Cfg::kRowBytes, 0, kSbo, kSw), idesc_pv,
-                        (j > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(&o_full[g]);
-          ++pc[g];
-          if (g == n_groups - 1) umma_commit(&v_empty[kc % kKvStages]);
-        };
+        for (int k = 0; k < HD / 16; ++k)
+          umma_f16_ss(tmem_base + g * 128, make_smem_desc(qa + k * 32, 0, kSbo, kSw),
+                      make_smem_desc(ka + k * 32, 0, kSbo, kSw), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+        ++sc;
+        umma_commit(&k_empty[kc % kKvStages]);
+        if (n_groups == 1) umma_commit(&k_empty[kc % kKvStages]);
+        if (j == kvb - 1) {  // last S of the item: its Q slot may go
+          umma_commit(&q_empty[item_i & 1]);
+          if (n_groups == 1) umma_commit(&q_empty[item_i & 1]);
+        }
+      };
+      auto issue_pv = [&](int n_groups, int j, int kc) {
+        mbar_wait(&p_full[g], pc & 1);
+        if (j == 0 && oc > 0) mbar_wait(&o_free[g], (oc - 1) & 1);  // previous item's O read out
+        mbar_wait(&v_full[kc % kKvStages], (kc / kKvStages) & 1);
+        tc_fence_after();
+        const int valid = min(128, p.Nk_main - j * 128);
+        const int ksteps = (valid + 15) >> 4;
+        const uint32_t va = v_addr + (kc % kKvStages) * Cfg::kTileBytes;
+        for (int kk = 0; kk < ksteps; ++kk)
+          umma_f16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + kk * 8,
+                      make_smem_desc(va + kk * 16 * Cfg::kRowBytes, 0, kSbo, kSw), idesc_pv,
+                      (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&o_full[g]);
+        ++pc;
+        umma_commit(&v_empty[kc % kKvStages]);
+        if (n_groups == 1) umma_commit(&v_empty[kc % kKvStages]);
+        if (j == kvb - 1) ++oc;
+      };
 
-        mbar_wait(q_full, item_i & 1);
-        for (int g = 0; g < n_groups; ++g) issue_s(g, 0);
+      int kv_base = 0, item_i = 0;
+      bool s0_issued = false;  // S(item, 0) already issued as the previous item's look-ahead
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i, kv_base += kvb) {
+        const int n_groups = groups_of(item);
+        if (g >= n_groups) continue;  // the other issuer releases this item's slots for both
+        if (!s0_issued) {
+          mbar_wait(&q_full[item_i & 1], (item_i >> 1) & 1);
+          issue_s(n_groups, item_i, 0, kv_base);
+        }
+        s0_issued = false;
+        const int next = item + gridDim.x;
         for (int j = 0; j < kvb; ++j) {
-          if (j + 1 < kvb)
-            for (int g = 0; g < n_groups; ++g) issue_s(g, j + 1);
-          for (int g = 0; g < n_groups; ++g) issue_pv(g, j);
+          if (j + 1 < kvb) {
+            issue_s(n_groups, item_i, j + 1, kv_base + j + 1);
+          } else if (next < n_items && g < groups_of(next)) {
+            mbar_wait(&q_full[(item_i + 1) & 1], ((item_i + 1) >> 1) & 1);
+            issue_s(groups_of(next), item_i + 1, 0, kv_base + kvb);
+            s0_issued = true;
+          }
+          issue_pv(n_groups, j, kv_base + j);
         }
       }
     }
-  } else {
-    // ---------------------------------------------------------------- softmax / epilogue
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+  } else if (warp < 12) {
+    // ---------------------------------------------------------------- softmax
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int g = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                    // row inside the tile == TMEM lane
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * 128;
-    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256 + g * 64;
-    uint8_t* p_row = smem + Cfg::kOffP + g * Cfg::kPBytes + r * 128;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_off + g * 128;
+    const uint32_t t_o = tmem_base + lane_off + 256 + g * 64;
+    const uint32_t t_p = tmem_base + lane_off + 384 + g * 64;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    int cnt = 0;  // running count of key blocks this group has processed (barrier phases)
+    // The two groups are symmetric, so whatever phase offset they start with persists.  Started
+    // together they exponentiate at the same time and fight for the MUFU, then both leave it idle;
+    // delaying group 1 once by about half a key block interleaves them.
+    if (g == 1 && p.stagger > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.stagger) {
+      }
+    }
+    int cnt = 0;   // key blocks this group has processed (phases of s_full / o_full)
+    int ic = 0;    // items this group has processed     (stats slot / phases of stats_full, o_free)
     int item_i = 0;
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i) {
       const int pair = item % p.q_pairs;
-      const int bh = item / p.q_pairs;
-      const int h = bh % p.H, b = bh / p.H;
       if (pair * 2 + g >= p.q_tiles) continue;            // this group has no tile in the item
-      const int qrow = (pair * 2 + g) * 128 + r;          // query index inside this (b, h)
       const bool warp_live = (pair * 2 + g) * 128 + quarter * 32 < p.Nq_main;
       float m_run = -INFINITY;
       float l_run = 0.f;
 
-      // Peeled key tail (HD == 64 only, host-guaranteed kv_blocks >= 2 so the Q tile outlives this
-      // read): s_tail[t] = <q_row, k_tail_t> on CUDA cores, q from the swizzled smem tile, k broadcast
-      // from global.  The scores join the LAST key block's max / sum; P_tail V_tail is added to O in
-      // the epilogue.
+      // Peeled key tail (HD == 64, host-guaranteed kv_blocks >= 2 so the Q slot outlives this read):
+      // s_tail[t] = <q_row, k_tail_t> on CUDA cores, q from the swizzled smem tile, k_tail broadcast
+      // from the item's tail slot.  The scores join the LAST key block's max / sum.
       float s_tail[kMaxTail];
 #pragma unroll
       for (int t = 0; t < kMaxTail; ++t) s_tail[t] = -INFINITY;
       if constexpr (HD == 64) {
         if (p.k_tail > 0) {
-          mbar_wait(q_full, item_i & 1);
-          const uint32_t q_row_addr = smem_u32(smem + Cfg::kOffQ + g * Cfg::kTileBytes + r * 128);
+          mbar_wait(&q_full[item_i & 1], (item_i >> 1) & 1);
+          const uint32_t q_row_addr =
+              smem_u32(smem + Cfg::kOffQ + ((item_i & 1) * 2 + g) * Cfg::kTileBytes + r * 128);
+          const uint32_t k_tail_addr = smem_u32(smem + Cfg::kOffTail + (item_i & 1) * Cfg::kTailSlotBytes);
 #pragma unroll
           for (int t = 0; t < kMaxTail; ++t) {
             if (t >= p.k_tail) break;
-            const uint4* krow = reinterpret_cast<const uint4*>(
-                p.k + (static_cast<long long>(b) * p.Nk + p.Nk_main + t) * p.ldk + h * HD);
             float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const float4 qv = lds128(q_row_addr + ((static_cast<uint32_t>(c) ^ sw) << 4));
-              const uint4 kv4 = __ldg(krow + c);
-              const float2 q0 = unpack_bf16x2(__float_as_uint(qv.x)), k0 = unpack_bf16x2(kv4.x);
-              const float2 q1 = unpack_bf16x2(__float_as_uint(qv.y)), k1 = unpack_bf16x2(kv4.y);
-              const float2 q2 = unpack_bf16x2(__float_as_uint(qv.z)), k2 = unpack_bf16x2(kv4.z);
-              const float2 q3 = unpack_bf16x2(__float_as_uint(qv.w)), k3 = unpack_bf16x2(kv4.w);
+              const float4 kv4 = lds128(k_tail_addr + t * 128 + c * 16);
+              const float2 q0 = unpack_bf16x2(__float_as_uint(qv.x)), k0 = unpack_bf16x2(__float_as_uint(kv4.x));
+              const float2 q1 = unpack_bf16x2(__float_as_uint(qv.y)), k1 = unpack_bf16x2(__float_as_uint(kv4.y));
+              const float2 q2 = unpack_bf16x2(__float_as_uint(qv.z)), k2 = unpack_bf16x2(__float_as_uint(kv4.z));
+              const float2 q3 = unpack_bf16x2(__float_as_uint(qv.w)), k3 = unpack_bf16x2(__float_as_uint(kv4.w));
               acc0 = fmaf(q0.x, k0.x, acc0); acc1 = fmaf(q0.y, k0.y, acc1);
               acc0 = fmaf(q1.x, k1.x, acc0); acc1 = fmaf(q1.y, k1.y, acc1);
               acc0 = fmaf(q2.x, k2.x, acc0); acc1 = fmaf(q2.y, k2.y, acc1);
@@ -307,15 +495,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_arrive(&s_free[g]);
 
         float alpha = 1.f;
-        float m_new = m_run;
+        bool rescale = false;
         if (warp_live) {
           float mx0 = -INFINITY, mx1 = -INFINITY;
           if (full_block) {
+            float mx[8];  // 8 independent chains: the FMNMX latency, not its throughput, is what shows
 #pragma unroll
-            for (int i = 0; i < 128; i += 2) {
-              mx0 = fmaxf(mx0, __uint_as_float(sreg[i]));
-              mx1 = fmaxf(mx1, __uint_as_float(sreg[i + 1]));
+            for (int a = 0; a < 8; ++a) mx[a] = fmaxf(__uint_as_float(sreg[a]), __uint_as_float(sreg[a + 8]));
+#pragma unroll
+            for (int i = 16; i < 128; i += 16) {
+#pragma unroll
+              for (int a = 0; a < 8; ++a)
+                mx[a] = fmaxf(mx[a], fmaxf(__uint_as_float(sreg[i + a]), __uint_as_float(sreg[i + a + 8])));
             }
+            mx0 = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            mx1 = fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]));
           } else {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -330,102 +524,109 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
             for (int t = 0; t < kMaxTail; ++t) mx0 = fmaxf(mx0, s_tail[t]);  // -inf when unused
           }
-          m_new = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
-          alpha = fast_exp2(m_run - m_new);
-          // exponentiate in registers first (sreg[i/2] <- packed bf16 pair), so that the wait for the
-          // previous block's P V (which still reads the P tile and writes O) comes as late as possible
-          l_run *= alpha;
-          float sum0 = 0.f, sum1 = 0.f;
-          const float neg_m = -m_new;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < nchunks) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const int idx = c * 32 + i;
-                float x0, x1;
-                ffma2(x0, x1, __uint_as_float(sreg[idx]), __uint_as_float(sreg[idx + 1]), p.scale_log2,
-                      p.scale_log2, neg_m, neg_m);
-                float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
-                if (!full_block) {
-                  if (idx >= valid) e0 = 0.f;
-                  if (idx + 1 >= valid) e1 = 0.f;
-                }
-                fadd2(sum0, sum1, sum0, sum1, e0, e1);
-                sreg[idx >> 1] = pack_bf16x2(e0, e1);
-              }
-            }
+          const float m_cand = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
+          if (j == 0) {
+            m_run = m_cand;  // nothing accumulated yet: P V(0) overwrites O
+          } else if (__any_sync(0xffffffffu, m_cand > m_run + kLazyMaxLog2)) {
+            alpha = fast_exp2(m_run - m_cand);
+            l_run *= alpha;
+            m_run = m_cand;
+            rescale = true;
           }
+          const float neg_m = -m_run;
+          float sum = full_block ? exp_row<true, POLY>(sreg, p.scale_log2, neg_m, valid, nchunks)
+                                 : exp_row<false, POLY>(sreg, p.scale_log2, neg_m, valid, nchunks);
           if (HD == 64 && j == kvb - 1) {
 #pragma unroll
             for (int t = 0; t < kMaxTail; ++t) {
               e_tail[t] = fast_exp2(fmaf(s_tail[t], p.scale_log2, neg_m));  // exp2(-inf) = 0
-              sum0 += e_tail[t];
+              sum += e_tail[t];
             }
           }
-          l_run += sum0 + sum1;
-          m_run = m_new;
+          l_run += sum;
         }
-        if (j > 0) {
-          mbar_wait(&o_full[g], (cnt - 1) & 1);  // P_g and O_g are free again
+        if (cnt > 0) {
+          mbar_wait(&o_full[g], (cnt - 1) & 1);  // previous P V of this group retired: P_g free, O_g stable
           tc_fence_after();
-          if (warp_live && __any_sync(0xffffffffu, alpha != 1.f)) {
+        }
+        if (rescale) {  // warp-uniform, rare
 #pragma unroll
-            for (int c = 0; c < HD / 32; ++c) {
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(t_o + c * 32, v);
-              tmem_ld_wait();
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_o + c * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-              tmem_st_32x32b_x32(t_o + c * 32, v);
-            }
-            tmem_st_wait();
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x32(t_o + c * 32, v);
           }
         }
         if (warp_live) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < nchunks) {
-              uint8_t* dst = p_row + (c >> 1) * 16384;
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int w0 = c * 16 + t * 4;  // packed words of columns c*32 + t*8 .. +7
-                const uint32_t c8 = static_cast<uint32_t>((c & 1) * 4 + t);
-                *reinterpret_cast<uint4*>(dst + ((c8 ^ sw) << 4)) =
-                    make_uint4(sreg[w0], sreg[w0 + 1], sreg[w0 + 2], sreg[w0 + 3]);
-              }
-            }
-          }
+          for (int c = 0; c < 4; ++c)
+            if (c < nchunks) tmem_st_32x32b_x16_p(t_p + c * 16, sreg + c * 16);
         }
+        tmem_st_wait();
         tc_fence_before();
-        fence_proxy_async_smem();
         mbar_arrive(&p_full[g]);
       }
 
-      // epilogue: O / l -> bf16 -> global, one 2*HD-byte row per thread
-      mbar_wait(&o_full[g], (cnt - 1) & 1);
-      tc_fence_after();
-      if (warp_live) {
-        const float inv_l = 1.f / l_run;
-        __nv_bfloat16* orow =
-            p.out + (static_cast<long long>(b) * p.Nq + qrow) * p.ldo + h * HD;
+      // row statistics for the epilogue warps (double-buffered by this group's item parity)
+      if (ic > 0) mbar_wait(&o_free[g], (ic - 1) & 1);  // keeps stats_full at most one phase ahead
+      {
+        float* st = stats + ((ic & 1) * 2 + g) * (Cfg::kStatFields * 128);
+        st[0 * 128 + r] = 1.f / l_run;
+        st[1 * 128 + r] = (m_run + log2f(l_run)) * 0.6931471805599453f;
 #pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_o + c * 32, v);
+        for (int t = 0; t < kMaxTail; ++t) st[(2 + t) * 128 + r] = e_tail[t];
+      }
+      mbar_arrive(&stats_full[g]);
+      ++ic;
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    int ic[2] = {0, 0};
+    int pcnt[2] = {0, 0};
+    int item_i = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i) {
+      const int pair = item % p.q_pairs;
+      const int bh = item / p.q_pairs;
+      const int h = bh % p.H, b = bh / p.H;
+      const int n_groups = groups_of(item);
+      if (HD == 64 && p.k_tail > 0) mbar_wait(&q_full[item_i & 1], (item_i >> 1) & 1);
+      const uint32_t v_tail_addr =
+          smem_u32(smem + Cfg::kOffTail + (item_i & 1) * Cfg::kTailSlotBytes + kMaxTail * 128);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (g >= n_groups) break;
+        const int qrow = (pair * 2 + g) * 128 + r;
+        const float* st = stats + ((ic[g] & 1) * 2 + g) * (Cfg::kStatFields * 128);
+        mbar_wait(&stats_full[g], ic[g] & 1);
+        pcnt[g] += kvb;
+        mbar_wait(&o_full[g], (pcnt[g] - 1) & 1);  // the item's last P V retired
+        tc_fence_after();
+        const float inv_l = st[0 * 128 + r];
+        const bool row_ok = qrow < p.Nq_main;
+        const uint32_t t_o = tmem_base + lane_off + 256 + g * 64;
+        __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Nq + qrow) * p.ldo + h * HD;
+#pragma unroll
+        for (int c = 0; c < HD / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_o + c * 16, v);
           tmem_ld_wait();
           if constexpr (HD == 64) {
 #pragma unroll
             for (int t = 0; t < kMaxTail; ++t) {  // O += p_tail * v_tail (peeled keys)
               if (t >= p.k_tail) break;
-              const uint4* vrow = reinterpret_cast<const uint4*>(
-                  p.v + (static_cast<long long>(b) * p.Nk + p.Nk_main + t) * p.ldv + h * HD + c * 32);
-              const float e = e_tail[t];
+              const float e = st[(2 + t) * 128 + r];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const uint4 vv = __ldg(vrow + u);
-                const float2 a0 = unpack_bf16x2(vv.x), a1 = unpack_bf16x2(vv.y),
-                             a2 = unpack_bf16x2(vv.z), a3 = unpack_bf16x2(vv.w);
+              for (int u = 0; u < 2; ++u) {
+                const float4 vv = lds128(v_tail_addr + t * 128 + c * 32 + u * 16);
+                const float2 a0 = unpack_bf16x2(__float_as_uint(vv.x)), a1 = unpack_bf16x2(__float_as_uint(vv.y)),
+                             a2 = unpack_bf16x2(__float_as_uint(vv.z)), a3 = unpack_bf16x2(__float_as_uint(vv.w));
                 v[u * 8 + 0] = __float_as_uint(fmaf(e, a0.x, __uint_as_float(v[u * 8 + 0])));
                 v[u * 8 + 1] = __float_as_uint(fmaf(e, a0.y, __uint_as_float(v[u * 8 + 1])));
                 v[u * 8 + 2] = __float_as_uint(fmaf(e, a1.x, __uint_as_float(v[u * 8 + 2])));
@@ -437,27 +638,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               }
             }
           }
-          if (qrow < p.Nq_main) {
+          if (row_ok) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < 2; ++t) {
               uint4 pk;
-              pk.x = pack_bf16x2(__uint_as_float(v[t * 8 + 0]) * inv_l,
-                                 __uint_as_float(v[t * 8 + 1]) * inv_l);
-              pk.y = pack_bf16x2(__uint_as_float(v[t * 8 + 2]) * inv_l,
-                                 __uint_as_float(v[t * 8 + 3]) * inv_l);
-              pk.z = pack_bf16x2(__uint_as_float(v[t * 8 + 4]) * inv_l,
-                                 __uint_as_float(v[t * 8 + 5]) * inv_l);
-              pk.w = pack_bf16x2(__uint_as_float(v[t * 8 + 6]) * inv_l,
-                                 __uint_as_float(v[t * 8 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + c * 32 + t * 8) = pk;
+              pk.x = pack_bf16x2(__uint_as_float(v[t * 8 + 0]) * inv_l, __uint_as_float(v[t * 8 + 1]) * inv_l);
+              pk.y = pack_bf16x2(__uint_as_float(v[t * 8 + 2]) * inv_l, __uint_as_float(v[t * 8 + 3]) * inv_l);
+              pk.z = pack_bf16x2(__uint_as_float(v[t * 8 + 4]) * inv_l, __uint_as_float(v[t * 8 + 5]) * inv_l);
+              pk.w = pack_bf16x2(__uint_as_float(v[t * 8 + 6]) * inv_l, __uint_as_float(v[t * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c * 16 + t * 8) = pk;
             }
           }
         }
-        if (p.lse != nullptr && qrow < p.Nq_main)
-          p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qrow] =
-              (m_run + log2f(l_run)) * 0.6931471805599453f;
+        if (p.lse != nullptr && row_ok)
+          p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qrow] = st[1 * 128 + r];
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[g]);
+        ++ic[g];
       }
-      tc_fence_before();  // O_g reads retire before the next item's first P V overwrites it
+      if (HD == 64 && p.k_tail > 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail_free[item_i & 1]);
+      }
     }
   }
 
@@ -466,7 +669,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // Peeled query rows [Nq_main, Nq) -- in MIRAGE the global token's query -- on CUDA cores.
@@ -553,7 +755,7 @@ attn_tail_rows_kernel(const AttnDev p) {
   }
 }
 
-template <int HD>
+template <int HD, int POLY>
 static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
   using Cfg = AttnCfg<HD>;
   CUtensorMap tq, tk, tv;
@@ -599,7 +801,15 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
   p.q_pairs = (p.q_tiles + 1) / 2;
   p.kv_blocks = (p.Nk_main + 127) / 128;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  auto kern = attn_fwd_kernel<HD>;
+  {
+    static int stagger = -1;
+    if (stagger < 0) {
+      const char* e = getenv("MB_ATTN_STAGGER");
+      stagger = e ? atoi(e) : kDefaultStagger;
+    }
+    p.stagger = stagger;
+  }
+  auto kern = attn_fwd_kernel<HD, POLY>;
   static bool configured = false;
   if (!configured) {
     MB_CHECK_CUDA(
@@ -632,6 +842,20 @@ extern "C" int mb_attn_fwd(const mb_attn_args* a, void* stream_) {
              a->head_dim);
   MB_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0,
              "mb_attn_fwd: leading dimensions must be multiples of 8 elements");
-  if (a->head_dim == 64) return launch_attn_fwd<64>(a, stream);
-  return launch_attn_fwd<32>(a, stream);
+  // share of the exponentials evaluated on the FMA pipe (pairs out of every 16); tunable for
+  // experiments through MB_ATTN_POLY = 0 | 4 | 6 | 8
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("MB_ATTN_POLY");
+    poly = e ? atoi(e) : kDefaultPoly;
+  }
+  if (a->head_dim == 64) {
+    switch (poly) {
+      case 0: return launch_attn_fwd<64, 0>(a, stream);
+      case 6: return launch_attn_fwd<64, 6>(a, stream);
+      case 8: return launch_attn_fwd<64, 8>(a, stream);
+      default: return launch_attn_fwd<64, 4>(a, stream);
+    }
+  }
+  return launch_attn_fwd<32, 0>(a, stream);
 }

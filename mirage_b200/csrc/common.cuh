@@ -111,14 +111,18 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // Bounded wait: a protocol bug must never hang the GPU (a hung box is a lost box).  After ~4 s of
-// spinning the kernel traps, which surfaces as a CUDA error on the host.
+// spinning the kernel traps, which surfaces as a CUDA error on the host.  Build with
+// -DMB_DEBUG_BARRIERS to also print which barrier timed out (the printf call costs registers and
+// instruction-cache footprint at every wait site, so it is off by default).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 8000000000LL) {
-      printf("mirage_b200: mbarrier timeout block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x, parity);
+#ifdef MB_DEBUG_BARRIERS
+      printf("mirage_b200: mbarrier timeout block=(%d,%d,%d) thread=%d bar=0x%x parity=%u\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+#endif
       __trap();
     }
   }
@@ -405,6 +409,17 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+      "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
+      "r"(v[15])
+      : "memory");
+}
+
+// pointer form (v must index registers at compile time after unrolling)
+__device__ __forceinline__ void tmem_st_32x32b_x16_p(uint32_t taddr, const uint32_t* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
