@@ -159,14 +159,16 @@ int mb_layernorm_fwd(const float* x, const float* weight, const float* bias, voi
                      int64_t ldx, int64_t ldy, float eps, void* stream);
 
 /* LayerNorm backward.  dy bf16 or f32 (dy_dtype); dx f32 = LN'(dy) (+ dres if non-NULL: the gradient
- * arriving through the residual branch); dweight/dbias f32 [dim], overwritten or accumulated.
+ * arriving through the residual branch); dx_bf16 (optional, contiguous bf16 [rows, dim]) receives the
+ * same values rounded to bf16 -- the operand of the weight/data-gradient GEMMs that follow;
+ * dweight/dbias f32 [dim], overwritten or accumulated.
  * workspace: mb_layernorm_bwd_workspace(rows, dim) bytes of device memory. */
 int64_t mb_layernorm_bwd_workspace(int64_t rows, int64_t dim);
 int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* weight,
                      const float* mean, const float* rstd, const float* dres, float* dx,
-                     float* dweight, float* dbias, int32_t accumulate, void* workspace,
-                     int64_t rows, int64_t dim, int64_t ldx, int64_t lddy, int64_t lddx,
-                     void* stream);
+                     void* dx_bf16, float* dweight, float* dbias, int32_t accumulate,
+                     void* workspace, int64_t rows, int64_t dim, int64_t ldx, int64_t lddy,
+                     int64_t lddx, void* stream);
 
 /* out[c] (+)= sum_r a[r, c] -- bias gradient of every nn.Linear on the path. */
 int64_t mb_colsum_workspace(int64_t rows, int64_t cols);

@@ -152,9 +152,10 @@ static __device__ __noinline__ void epi_generic_chunk(const GemmDev& p, float4 a
   }
   if (p.epilogue & MB_EPI_DGELU) {
     const uint2 pk = __ldg(reinterpret_cast<const uint2*>(p.aux_in + (long long)row * p.ld_aux + col));
-    const float2 h0 = unpack_bf16x2(pk.x), h1 = unpack_bf16x2(pk.y);
-    f0 *= gelu_erf_grad(h0.x); f1 *= gelu_erf_grad(h0.y);
-    f2 *= gelu_erf_grad(h1.x); f3 *= gelu_erf_grad(h1.y);
+    float2 h0 = unpack_bf16x2(pk.x), h1 = unpack_bf16x2(pk.y);
+    gelu_fast_grad2(h0.x, h0.y);
+    gelu_fast_grad2(h1.x, h1.y);
+    f0 *= h0.x; f1 *= h0.y; f2 *= h1.x; f3 *= h1.y;
   }
   if (p.residual != nullptr && first_split) {
     const long long rr = p.res_period > 0 ? row % p.res_period : row;
@@ -180,11 +181,7 @@ static __device__ __noinline__ void epi_generic_chunk(const GemmDev& p, float4 a
     oidx = orow * p.ldc + col;
   }
   if (p.epilogue & MB_EPI_ATOMIC) {
-    float* o = reinterpret_cast<float*>(p.out) + oidx;
-    atomicAdd(o + 0, f0);
-    atomicAdd(o + 1, f1);
-    atomicAdd(o + 2, f2);
-    atomicAdd(o + 3, f3);
+    red_add_v4(reinterpret_cast<float*>(p.out) + oidx, f0, f1, f2, f3);  // oidx % 4 == 0 (ldc % 8, col % 4)
   } else if (p.out_f32) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + oidx) = make_float4(f0, f1, f2, f3);
   } else {
@@ -275,9 +272,10 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
           gelu_fast2(f0, f1); gelu_fast2(f2, f3);
         }
         if constexpr (MODE == EPI_DGELU) {
-          const float2 h0 = unpack_bf16x2(cur.aux[it].x), h1 = unpack_bf16x2(cur.aux[it].y);
-          f0 *= gelu_erf_grad(h0.x); f1 *= gelu_erf_grad(h0.y);
-          f2 *= gelu_erf_grad(h1.x); f3 *= gelu_erf_grad(h1.y);
+          float2 h0 = unpack_bf16x2(cur.aux[it].x), h1 = unpack_bf16x2(cur.aux[it].y);
+          gelu_fast_grad2(h0.x, h0.y);
+          gelu_fast_grad2(h1.x, h1.y);
+          f0 *= h0.x; f1 *= h0.y; f2 *= h1.x; f3 *= h1.y;
         }
         if constexpr (MODE == EPI_RES) {
           f0 += cur.res[it].x; f1 += cur.res[it].y; f2 += cur.res[it].z; f3 += cur.res[it].w;
@@ -286,10 +284,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
           if constexpr (OUT_BYTES == 4) {
             float* o = reinterpret_cast<float*>(optr + it * ostep);
             if (atomic) {
-              atomicAdd(o + 0, f0);
-              atomicAdd(o + 1, f1);
-              atomicAdd(o + 2, f2);
-              atomicAdd(o + 3, f3);
+              red_add_v4(o, f0, f1, f2, f3);
             } else {
               *reinterpret_cast<float4*>(o) = make_float4(f0, f1, f2, f3);
             }

@@ -73,77 +73,87 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
 // LayerNorm backward.  dy is bf16 (gradient of the GEMM operand) or fp32.
 //   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w
 //   optionally dx += dres (the gradient flowing through the residual connection, fp32)
-// Per-block partial sums of dw = sum dy * xhat and db = sum dy go to part[blk, 2, D]; a second
-// kernel reduces them (deterministic, no atomics).
+//   optionally dx is ALSO written as bf16 (dx_bf16): the operand of the wgrad / dgrad GEMMs that
+//   consume it next, so no separate cast kernel ever re-reads dx.
+// Persistent blocks (2 per SM); every warp walks rows with a grid stride and accumulates its
+// dw = sum dy * xhat, db = sum dy partials in its own shared-memory slab (registers hold only the row
+// being processed, so two blocks fit per SM without spills).
+// Per-block partials go to part[blk, 2, D]; a second kernel reduces them (deterministic, no atomics).
 template <int VPL, bool DY_BF16>
-__global__ void __launch_bounds__(kRowThreads)
+__global__ void __launch_bounds__(kRowThreads, 2)
 layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ w, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, const float* __restrict__ dres,
-                     float* __restrict__ dx, float* __restrict__ part, long long M, int D,
-                     long long ldx, long long lddy, long long lddx, int rows_per_block) {
+                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
+                     float* __restrict__ part, long long M, int D, long long ldx, long long lddy,
+                     long long lddx) {
   extern __shared__ float sred[];  // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 aw[VPL], ab[VPL];
+  float* sw = sred + warp * 2 * D;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    aw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int col = (i * 32 + lane) * 4;
+    st4(sw + col, make_float4(0.f, 0.f, 0.f, 0.f));
+    st4(sw + D + col, make_float4(0.f, 0.f, 0.f, 0.f));
   }
-  const long long row0 = (long long)blockIdx.x * rows_per_block;
-  for (int rr = warp; rr < rows_per_block; rr += kRowThreads / 32) {
-    const long long row = row0 + rr;
-    if (row >= M) break;
+  const float invD = 1.f / D;
+  for (long long row = (long long)blockIdx.x * (kRowThreads / 32) + warp; row < M;
+       row += (long long)gridDim.x * (kRowThreads / 32)) {
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float4 xh[VPL], g[VPL];
+    float4 xh[VPL], d[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int col = (i * 32 + lane) * 4;
-      const float4 xv = ld4(x + row * ldx + col);
-      float4 d;
+      xh[i] = ld4(x + row * ldx + col);
       if (DY_BF16) {
         const uint2 pk = *reinterpret_cast<const uint2*>(
             reinterpret_cast<const __nv_bfloat16*>(dy) + row * lddy + col);
         const float2 a = unpack_bf16x2(pk.x), c = unpack_bf16x2(pk.y);
-        d = make_float4(a.x, a.y, c.x, c.y);
+        d[i] = make_float4(a.x, a.y, c.x, c.y);
       } else {
-        d = ld4(reinterpret_cast<const float*>(dy) + row * lddy + col);
+        d[i] = ld4(reinterpret_cast<const float*>(dy) + row * lddy + col);
       }
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + col));
-      xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd,
-                          (xv.w - mean) * rstd);
-      g[i] = make_float4(d.x * wv.x, d.y * wv.y, d.z * wv.z, d.w * wv.w);
-      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-      s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-      aw[i].x += d.x * xh[i].x; aw[i].y += d.y * xh[i].y;
-      aw[i].z += d.z * xh[i].z; aw[i].w += d.w * xh[i].w;
-      ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
     }
-    const float m1 = warp_sum(s1) / D, m2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + col));
+      xh[i] = make_float4((xh[i].x - mean) * rstd, (xh[i].y - mean) * rstd, (xh[i].z - mean) * rstd,
+                          (xh[i].w - mean) * rstd);
+      // parameter-gradient partials (own slab: no conflicts, no atomics)
+      float4 a = ld4(sw + col), b = ld4(sw + D + col);
+      a.x += d[i].x * xh[i].x; a.y += d[i].y * xh[i].y; a.z += d[i].z * xh[i].z; a.w += d[i].w * xh[i].w;
+      b.x += d[i].x; b.y += d[i].y; b.z += d[i].z; b.w += d[i].w;
+      st4(sw + col, a);
+      st4(sw + D + col, b);
+      d[i] = make_float4(d[i].x * wv.x, d[i].y * wv.y, d[i].z * wv.z, d[i].w * wv.w);  // g = dy * w
+      s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
+    }
+    const float m1 = warp_sum(s1) * invD, m2 = warp_sum(s2) * invD;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int col = (i * 32 + lane) * 4;
       float4 o;
-      o.x = rstd * (g[i].x - m1 - xh[i].x * m2);
-      o.y = rstd * (g[i].y - m1 - xh[i].y * m2);
-      o.z = rstd * (g[i].z - m1 - xh[i].z * m2);
-      o.w = rstd * (g[i].w - m1 - xh[i].w * m2);
+      o.x = rstd * (d[i].x - m1 - xh[i].x * m2);
+      o.y = rstd * (d[i].y - m1 - xh[i].y * m2);
+      o.z = rstd * (d[i].z - m1 - xh[i].z * m2);
+      o.w = rstd * (d[i].w - m1 - xh[i].w * m2);
       if (dres) {
         const float4 r = ld4(dres + row * lddx + col);
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       st4(dx + row * lddx + col, o);
+      if (dx_bf16) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(dx_bf16 + row * (long long)D + col) = pk;
+      }
     }
   }
   // block reduction of the parameter-gradient partials
-  float* sw = sred + warp * 2 * D;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int col = (i * 32 + lane) * 4;
-    st4(sw + col, aw[i]);
-    st4(sw + D + col, ab[i]);
-  }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * D; c += kRowThreads) {
     float acc = 0.f;
@@ -153,51 +163,96 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
   }
 }
 
-// out[c] (+)= sum_r part[r, c]   (c < cols); one thread per column, coalesced across threads
-__global__ void colsum_reduce_kernel(const float* __restrict__ part, float* __restrict__ out0,
-                                     float* __restrict__ out1, int rows, int D, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * D) return;
+// out[c] (+)= sum_r part[r, c]   (c < cols).  Block = 32 columns x 32 row lanes: the partial rows are
+// summed in parallel (a single thread per column walking hundreds of rows is a serial chain of
+// dependent-latency loads), then folded through shared memory.  out1 != NULL splits the columns into
+// two outputs of D each (LayerNorm dweight | dbias).
+__global__ void __launch_bounds__(1024)
+colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1,
+                    int rows, int cols, int D, int accumulate) {
+  __shared__ float sm[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int r = 0; r < rows; ++r) acc += part[(long long)r * 2 * D + c];
-  float* o = (c < D) ? (out0 + c) : (out1 + (c - D));
-  *o = accumulate ? (*o + acc) : acc;
+  if (c < cols)
+    for (int r = threadIdx.y; r < rows; r += 32) acc += part[(long long)r * cols + c];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += sm[k][threadIdx.x];
+    float* o = (out1 == nullptr || c < D) ? (out0 + c) : (out1 + (c - D));
+    *o = accumulate ? (*o + t) : t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
-// column sums of a bf16 / fp32 matrix (bias gradients): part[blk, N] then reduce.
-// Each block walks rows_per_block rows; thread t owns 4 consecutive columns per 1024-column slab.
+// column sums of a bf16 / fp32 matrix (bias gradients): part[blk, N] then colsum_final_kernel.
+// Thread = one 16-byte column chunk (8 bf16 / 4 fp32) x one row lane; a block is CPB chunks wide and
+// 256 / CPB row lanes tall and walks rows_per_block rows with 8 independent 16-byte loads in flight
+// per thread; the row lanes are folded through shared memory, one partial row per block.
 // ------------------------------------------------------------------------------------------
 template <bool IN_BF16>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const void* __restrict__ a, float* __restrict__ part, long long M, int N,
-                      long long lda, int rows_per_block) {
+                      long long lda, int rows_per_block, int cpb) {
+  constexpr int EPC = IN_BF16 ? 8 : 4;  // elements per 16-byte chunk
+  __shared__ float sm[256 * 8];
+  const int lanes = 256 / cpb;
+  const int cx = threadIdx.x % cpb, ly = threadIdx.x / cpb;
+  const int chunk = blockIdx.y * cpb + cx;
+  const int col = chunk * EPC;
   const long long row0 = (long long)blockIdx.x * rows_per_block;
   const long long row1 = (row0 + rows_per_block < M) ? row0 + rows_per_block : M;
-  for (int col = (blockIdx.y * 256 + threadIdx.x) * 4; col < N; col += gridDim.y * 1024) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long r = row0; r < row1; ++r) {
-      if (IN_BF16) {
-        const uint2 pk = *reinterpret_cast<const uint2*>(
-            reinterpret_cast<const __nv_bfloat16*>(a) + r * lda + col);
-        const float2 u = unpack_bf16x2(pk.x), v = unpack_bf16x2(pk.y);
-        acc.x += u.x; acc.y += u.y; acc.z += v.x; acc.w += v.y;
-      } else {
-        const float4 v = ld4(reinterpret_cast<const float*>(a) + r * lda + col);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (col < N) {
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(a) + (size_t)col * (IN_BF16 ? 2 : 4);
+    const size_t ldb = (size_t)lda * (IN_BF16 ? 2 : 4);
+    long long r = row0 + ly;
+    for (; r + 7 * lanes < row1; r += 8 * lanes) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const uint4*>(base + (size_t)(r + u * lanes) * ldb);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (IN_BF16) {
+          const float2 f0 = unpack_bf16x2(v[u].x), f1 = unpack_bf16x2(v[u].y), f2 = unpack_bf16x2(v[u].z),
+                       f3 = unpack_bf16x2(v[u].w);
+          acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+          acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+        } else {
+          acc[0] += __uint_as_float(v[u].x); acc[1] += __uint_as_float(v[u].y);
+          acc[2] += __uint_as_float(v[u].z); acc[3] += __uint_as_float(v[u].w);
+        }
       }
     }
-    st4(part + (long long)blockIdx.x * N + col, acc);
+    for (; r < row1; r += lanes) {
+      const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)r * ldb);
+      if (IN_BF16) {
+        const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z),
+                     f3 = unpack_bf16x2(v.w);
+        acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+        acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+      } else {
+        acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y);
+        acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
+      }
+    }
   }
-}
-
-__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int rows,
-                                    int N, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
-  float acc = 0.f;
-  for (int r = 0; r < rows; ++r) acc += part[(long long)r * N + c];
-  out[c] = accumulate ? out[c] + acc : acc;
+#pragma unroll
+  for (int e = 0; e < EPC; ++e) sm[(ly * EPC + e) * cpb + cx] = acc[e];
+  __syncthreads();
+  if (ly == 0 && col < N) {
+    float* o = part + (long long)blockIdx.x * N + col;
+#pragma unroll
+    for (int e = 0; e < EPC; ++e) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += sm[(l * EPC + e) * cpb + cx];
+      o[e] = t;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -315,25 +370,31 @@ int mb_layernorm_fwd(const float* x, const float* weight, const float* bias, voi
   return launch_ln_fwd<false>(x, weight, bias, y, mean, rstd, rows, (int)dim, ldx, ldy, eps, st);
 }
 
+static int ln_bwd_blocks(int64_t rows) {
+  const int64_t need = (rows + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 2;
+  return (int)(need < cap ? need : cap);
+}
+
 int64_t mb_layernorm_bwd_workspace(int64_t rows, int64_t dim) {
-  const int64_t blocks = (rows + 63) / 64;
-  return blocks * 2 * dim * (int64_t)sizeof(float);
+  return (int64_t)ln_bwd_blocks(rows) * 2 * dim * (int64_t)sizeof(float);
 }
 
 int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* weight,
                      const float* mean, const float* rstd, const float* dres, float* dx,
-                     float* dweight, float* dbias, int32_t accumulate, void* workspace,
-                     int64_t rows, int64_t dim, int64_t ldx, int64_t lddy, int64_t lddx,
-                     void* stream) {
+                     void* dx_bf16, float* dweight, float* dbias, int32_t accumulate,
+                     void* workspace, int64_t rows, int64_t dim, int64_t ldx, int64_t lddy,
+                     int64_t lddx, void* stream) {
   MB_REQUIRE(dy && x && weight && mean && rstd && dx && dweight && dbias && workspace,
              "mb_layernorm_bwd: null pointer");
   MB_REQUIRE(dim % 128 == 0 && dim >= 128 && dim <= 1024,
              "mb_layernorm_bwd: dim=%lld unsupported (multiple of 128, <= 1024)", (long long)dim);
+  MB_REQUIRE(rows > 0, "mb_layernorm_bwd: rows must be positive");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int rpb = 64;
-  const unsigned grid = (unsigned)((rows + rpb - 1) / rpb);
+  const unsigned grid = (unsigned)ln_bwd_blocks(rows);
   const size_t smem = (size_t)8 * 2 * dim * sizeof(float);
   float* part = reinterpret_cast<float*>(workspace);
+  __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   const int D = (int)dim;
 #define MB_LNB(V, BF)                                                                              \
   {                                                                                                \
@@ -341,8 +402,8 @@ int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const flo
     if (smem > 48 * 1024)                                                                          \
       MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                          (int)smem));                                              \
-    kern<<<grid, kRowThreads, smem, st>>>(dy, x, weight, mean, rstd, dres, dx, part, rows, D, ldx, \
-                                          lddy, lddx, rpb);                                        \
+    kern<<<grid, kRowThreads, smem, st>>>(dy, x, weight, mean, rstd, dres, dx, dxb, part, rows, D, \
+                                          ldx, lddy, lddx);                                        \
   }
 #define MB_LNB2(V)                                                                                 \
   case V:                                                                                          \
@@ -355,32 +416,58 @@ int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const flo
 #undef MB_LNB2
 #undef MB_LNB
   MB_CHECK_CUDA(cudaGetLastError());
-  colsum_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(part, dweight, dbias, (int)grid, D,
-                                                             accumulate);
+  colsum_final_kernel<<<(2 * D + 31) / 32, dim3(32, 32), 0, st>>>(part, dweight, dbias, (int)grid,
+                                                                   2 * D, D, accumulate);
   MB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
+// tiling of mb_colsum: chunks per block, row blocks
+static void colsum_plan(int64_t rows, int64_t cols, int esize, int* cpb, int* grid_y, int* rpb,
+                        int* grid_x) {
+  const int epc = 16 / esize;
+  const int chunks = (int)((cols + epc - 1) / epc);
+  int c = 256;
+  while (c > 1 && c / 2 >= chunks) c /= 2;  // largest power of two <= 256 that still covers... (>= chunks)
+  *cpb = c;
+  *grid_y = (chunks + c - 1) / c;
+  const int lanes = 256 / c;
+  int target = (sm_count() * 4 + *grid_y - 1) / *grid_y;  // ~4 blocks per SM in total
+  int64_t r = (rows + target - 1) / target;
+  const int64_t min_r = (int64_t)lanes * 8;  // at least one full unrolled batch per thread
+  if (r < min_r) r = min_r;
+  *rpb = (int)r;
+  *grid_x = (int)((rows + r - 1) / r);
+}
+
 int64_t mb_colsum_workspace(int64_t rows, int64_t cols) {
-  const int64_t blocks = (rows + 255) / 256;
-  return blocks * cols * (int64_t)sizeof(float);
+  int cpb, gy, rpb, gx_bf16, gx_f32;
+  colsum_plan(rows, cols, 2, &cpb, &gy, &rpb, &gx_bf16);
+  colsum_plan(rows, cols, 4, &cpb, &gy, &rpb, &gx_f32);
+  const int gx = gx_bf16 > gx_f32 ? gx_bf16 : gx_f32;
+  return (int64_t)gx * cols * (int64_t)sizeof(float);
 }
 
 int mb_colsum(const void* a, int32_t a_dtype, float* out, int32_t accumulate, void* workspace,
               int64_t rows, int64_t cols, int64_t lda, void* stream) {
   MB_REQUIRE(a && out && workspace, "mb_colsum: null pointer");
-  MB_REQUIRE(cols % 4 == 0 && lda % 4 == 0, "mb_colsum: cols and lda must be multiples of 4");
+  MB_REQUIRE(rows > 0 && cols > 0, "mb_colsum: empty matrix");
+  const int esize = a_dtype == MB_BF16 ? 2 : 4;
+  MB_REQUIRE(cols % (16 / esize) == 0 && lda % (16 / esize) == 0,
+             "mb_colsum: cols and lda must be multiples of %d elements (16 bytes)", 16 / esize);
+  MB_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0, "mb_colsum: matrix must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int rpb = 256;
-  dim3 grid((unsigned)((rows + rpb - 1) / rpb), (unsigned)((cols + 1023) / 1024));
+  int cpb, gy, rpb, gx;
+  colsum_plan(rows, cols, esize, &cpb, &gy, &rpb, &gx);
+  dim3 grid((unsigned)gx, (unsigned)gy);
   float* part = reinterpret_cast<float*>(workspace);
   if (a_dtype == MB_BF16)
-    colsum_partial_kernel<true><<<grid, 256, 0, st>>>(a, part, rows, (int)cols, lda, rpb);
+    colsum_partial_kernel<true><<<grid, 256, 0, st>>>(a, part, rows, (int)cols, lda, rpb, cpb);
   else
-    colsum_partial_kernel<false><<<grid, 256, 0, st>>>(a, part, rows, (int)cols, lda, rpb);
+    colsum_partial_kernel<false><<<grid, 256, 0, st>>>(a, part, rows, (int)cols, lda, rpb, cpb);
   MB_CHECK_CUDA(cudaGetLastError());
-  colsum_final_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(part, out, (int)grid.x,
-                                                                       (int)cols, accumulate);
+  colsum_final_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 32), 0, st>>>(
+      part, out, nullptr, gx, (int)cols, (int)cols, accumulate);
   MB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -34,7 +34,8 @@ class _Bucket:
 
 class GradBucketAllReduce:
     def __init__(self, module: nn.Module, bucket_mb: float = 64.0,
-                 process_group: Optional[dist.ProcessGroup] = None, average: bool = True):
+                 process_group: Optional[dist.ProcessGroup] = None, average: bool = True,
+                 direct: bool = True):
         self.module = module
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -67,6 +68,22 @@ class GradBucketAllReduce:
                 self._owner[p] = b
                 p.register_post_accumulate_grad_hook(self._on_grad_ready)
         self.num_params = sum(b.flat.numel() for b in self.buckets)
+        # let the backward kernels accumulate straight into the bucket views (no temporary gradient,
+        # no per-parameter add kernel); see mirage_b200.functional.set_grad_sink
+        if direct and params[0].is_cuda:
+            from . import functional as Fn
+            Fn.set_grad_sink(self)
+
+    # -- gradient sink protocol ------------------------------------------------------------------
+    def target(self, p: torch.Tensor):
+        """fp32 buffer the backward kernels accumulate p's gradient into (None: not managed here)."""
+        if p not in self._owner:
+            return None
+        g = p.grad
+        return g if (g is not None and g.dtype == torch.float32 and g.is_contiguous()) else None
+
+    def done(self, p: torch.Tensor):
+        self._on_grad_ready(p)
 
     # -- hooks -----------------------------------------------------------------------------------
     def _on_grad_ready(self, p: torch.Tensor):

@@ -12,6 +12,7 @@ Every ``torch.autograd.Function`` here has a hand-written backward that calls th
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional, Sequence
 
 import torch
@@ -23,20 +24,23 @@ from . import ops
 # ---------------------------------------------------------------------------------------------
 # bf16 weight shadows
 # ---------------------------------------------------------------------------------------------
-_shadow: dict[int, tuple[int, int, torch.Tensor]] = {}
+_shadow: dict[int, tuple] = {}   # id(param) -> (weakref(param), version, data_ptr, bf16 copy)
 
 
 def bf16_weight(p: torch.Tensor) -> torch.Tensor:
-    """bf16 copy of an fp32 weight, cached until the parameter is modified in place or replaced."""
+    """bf16 copy of an fp32 weight, cached until the parameter is modified in place or replaced.
+    The entry is tied to the parameter OBJECT (weak reference): ids and allocator blocks are recycled
+    once a model is freed, so (id, version, data_ptr) alone can match a different, differently shaped
+    parameter of a later model."""
     if p.dtype == torch.bfloat16:
         return p
     key = id(p)
     ver = p._version
     ent = _shadow.get(key)
-    if ent is not None and ent[0] == ver and ent[1] == p.data_ptr():
-        return ent[2]
+    if ent is not None and ent[0]() is p and ent[1] == ver and ent[2] == p.data_ptr():
+        return ent[3]
     w = ops.cast_bf16(p.detach().contiguous())
-    _shadow[key] = (ver, p.data_ptr(), w)
+    _shadow[key] = (weakref.ref(p, lambda _r, k=key: _shadow.pop(k, None)), ver, p.data_ptr(), w)
     return w
 
 
@@ -50,9 +54,26 @@ def grad_needed(*tensors) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
+# bf16 twin of the most recent fp32 gradient a LayerNorm-backward kernel produced: the kernel writes
+# both, and the consumer (the next block's backward, or the GEMMs right after) asks for the bf16 view
+# through _as_bf16 without a cast kernel re-reading the fp32 tensor.  The fp32 tensor is kept alive
+# by the entry, so its storage cannot be recycled for a look-alike while the entry exists.
+_twin: dict = {"src": None, "ver": -1, "bf16": None}
+
+
+def _remember_twin(src: torch.Tensor, bf16: torch.Tensor):
+    _twin["src"], _twin["ver"], _twin["bf16"] = src, src._version, bf16
+
+
 def _as_bf16(t: torch.Tensor) -> torch.Tensor:
     if t.dtype == torch.bfloat16:
         return t if t.stride(-1) == 1 else t.contiguous()
+    src = _twin["src"]
+    if (src is not None and t.data_ptr() == src.data_ptr() and t.shape == src.shape
+            and t.stride() == src.stride() and t._version == _twin["ver"]):
+        out = _twin["bf16"]
+        _twin["src"] = _twin["bf16"] = None
+        return out
     return ops.cast_bf16(t.contiguous())
 
 
@@ -64,11 +85,50 @@ def _wgrad_splits(n_out: int, k_in: int, tokens: int) -> int:
     return max(1, s)
 
 
-def wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """dW[n_out, k_in] = dy[T, n_out]^T x[T, k_in] in fp32 (split-K over tokens with atomics)."""
+# ---------------------------------------------------------------------------------------------
+# gradient sink: parameter gradients written straight into their final buffers
+# ---------------------------------------------------------------------------------------------
+# A data-parallel trainer keeps every ``param.grad`` as a view into a flat all-reduce bucket
+# (mirage_b200/ddp.py).  When such a sink is registered, the backward kernels ACCUMULATE into that
+# view (wgrad: vector reductions in the GEMM epilogue; bias / LayerNorm grads: accumulate flag) and
+# the autograd node returns ``None`` for the parameter, so the engine neither materialises a
+# temporary gradient nor launches an add kernel per parameter; the sink is told when the gradient
+# is complete (it may then launch the bucket's all-reduce).  Without a sink nothing changes.
+_grad_sink = None
+
+
+def set_grad_sink(sink):
+    """sink.target(param) -> fp32 tensor to accumulate into (or None); sink.done(param)."""
+    global _grad_sink
+    _grad_sink = sink
+
+
+def _sink_of(param):
+    s = _grad_sink
+    if s is None or param is None or not param.requires_grad:
+        return None
+    return s.target(param)
+
+
+def _done(param, tgt, value):
+    """Returns what the autograd node should hand back for ``param``."""
+    if tgt is None:
+        return value
+    _grad_sink.done(param)
+    return None
+
+
+def wgrad(dy: torch.Tensor, x: torch.Tensor, into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW[n_out, k_in] = dy[T, n_out]^T x[T, k_in] in fp32 (split-K over tokens with atomics).
+    ``into``: accumulate into this [n_out, k_in]-shaped fp32 buffer instead of returning a new one."""
     T, n_out = dy.shape
     k_in = x.shape[1]
     splits = _wgrad_splits(n_out, k_in, T)
+    if into is not None:
+        out = into.view(n_out, k_in)
+        ops.gemm(dy, x, m=n_out, n=k_in, k=T, a_layout=L.MB_MAJOR_MN, b_layout=L.MB_MAJOR_MN, out=out,
+                 k_splits=splits, atomic=True)
+        return out
     if splits > 1:
         out = torch.zeros((n_out, k_in), dtype=torch.float32, device=dy.device)
     else:
@@ -293,29 +353,39 @@ class _Block(Function):
         D = heads * hd
         dx2 = dx2.contiguous()
         dyb = _as_bf16(dx2)
+        ps = (n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
+        tg = [_sink_of(q) for q in ps]
         # MLP branch
-        d_fc2_w = wgrad(dyb, g)
-        d_fc2_b = ops.colsum(dyb)
+        d_fc2_w = wgrad(dyb, g, into=tg[10])
+        d_fc2_b = ops.colsum(dyb, into=tg[11])
         dpre = dgrad(dyb, bf16_weight(fc2_w), dgelu_aux=pre)
-        d_fc1_w = wgrad(dpre, h2)
-        d_fc1_b = ops.colsum(dpre)
+        d_fc1_w = wgrad(dpre, h2, into=tg[8])
+        d_fc1_b = ops.colsum(dpre, into=tg[9])
         dh2 = dgrad(dpre, bf16_weight(fc1_w))
-        dx1, d_n2w, d_n2b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2)
+        dx1, dx1b, d_n2w, d_n2b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2, want_bf16=True,
+                                                    dw_into=tg[6], db_into=tg[7])
         # attention branch
-        dx1b = _as_bf16(dx1)
-        d_proj_w = wgrad(dx1b, a)
-        d_proj_b = ops.colsum(dx1b)
+        d_proj_w = wgrad(dx1b, a, into=tg[4])
+        d_proj_b = ops.colsum(dx1b, into=tg[5])
         da = dgrad(dx1b, bf16_weight(proj_w))
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], a, da, lse,
                           dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
                           batch=B, heads=heads, nq=N, nk=N, head_dim=hd, scale=hd ** -0.5)
-        d_qkv_w = wgrad(dqkv, h1)
-        d_qkv_b = ops.colsum(dqkv)
+        d_qkv_w = wgrad(dqkv, h1, into=tg[2])
+        d_qkv_b = ops.colsum(dqkv, into=tg[3])
         dh1 = dgrad(dqkv, bf16_weight(qkv_w))
-        dx, d_n1w, d_n1b = ops.layernorm_bwd(dh1, x, n1w, mean1, rstd1, dres=dx1)
-        return (dx, None, None, None, None, None, d_n1w, d_n1b, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b,
-                d_n2w, d_n2b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b)
+        dx, dxb, d_n1w, d_n1b = ops.layernorm_bwd(dh1, x, n1w, mean1, rstd1, dres=dx1, want_bf16=True,
+                                                  dw_into=tg[0], db_into=tg[1])
+        _remember_twin(dx, dxb)  # the previous block's backward starts by casting exactly this tensor
+        grads = (d_n1w, d_n1b, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, d_n2w, d_n2b, d_fc1_w, d_fc1_b,
+                 d_fc2_w, d_fc2_b)
+        # completion is reported in the order the gradients were produced (output side first), which
+        # is the order the all-reduce buckets were laid out in
+        out = [None] * 12
+        for i in (10, 11, 8, 9, 6, 7, 4, 5, 2, 3, 0, 1):
+            out[i] = _done(ps[i], tg[i], grads[i])
+        return (dx, None, None, None, None, None, *out)
 
 
 def transformer_block(x, B, N, heads, eps, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b,

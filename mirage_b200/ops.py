@@ -183,33 +183,43 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: fl
 
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, mean: torch.Tensor,
-                  rstd: torch.Tensor, dres: torch.Tensor | None = None):
-    """Returns (dx f32, dweight f32, dbias f32); dx includes dres when given."""
+                  rstd: torch.Tensor, dres: torch.Tensor | None = None, want_bf16: bool = False,
+                  dw_into: torch.Tensor | None = None, db_into: torch.Tensor | None = None):
+    """Returns (dx f32, dweight f32, dbias f32); dx includes dres when given.  With ``want_bf16`` the
+    kernel also writes dx rounded to bf16 and (dx, dx_bf16, dweight, dbias) is returned."""
     _req_cuda(dy, x, weight, mean, rstd, dres)
     rows, dim = x.shape
     dx = torch.empty((rows, dim), dtype=torch.float32, device=x.device)
-    dw = torch.empty(dim, dtype=torch.float32, device=x.device)
-    db = torch.empty(dim, dtype=torch.float32, device=x.device)
+    dxb = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    # dw_into / db_into: ACCUMULATE the parameter gradients into these fp32 [dim] buffers (both or neither)
+    acc = dw_into is not None and db_into is not None
+    dw = dw_into if acc else torch.empty(dim, dtype=torch.float32, device=x.device)
+    db = db_into if acc else torch.empty(dim, dtype=torch.float32, device=x.device)
     ws = torch.empty(L.lib().mb_layernorm_bwd_workspace(rows, dim), dtype=torch.uint8, device=x.device)
-    nbytes = rows * dim * (dy.element_size() + 4.0 + 4.0 + (4.0 if dres is not None else 0.0))
+    nbytes = rows * dim * (dy.element_size() + 4.0 + 4.0 + (4.0 if dres is not None else 0.0) +
+                           (2.0 if want_bf16 else 0.0))
     with _rec("layernorm_bwd", nbytes, "byte", kernels=2):
         L.check(L.lib().mb_layernorm_bwd(dy.data_ptr(), L.MB_BF16 if dy.dtype == torch.bfloat16 else L.MB_F32,
                                          x.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                         _ptr(dres), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), 0,
+                                         _ptr(dres), dx.data_ptr(), _ptr(dxb), dw.data_ptr(), db.data_ptr(), 1 if acc else 0,
                                          ws.data_ptr(), rows, dim, x.stride(0), dy.stride(0), dx.stride(0),
                                          _stream()), "mb_layernorm_bwd")
+    if want_bf16:
+        return dx, dxb, dw, db
     return dx, dw, db
 
 
-def colsum(a: torch.Tensor) -> torch.Tensor:
-    """fp32 column sums of a 2-D bf16/f32 matrix (bias gradient)."""
+def colsum(a: torch.Tensor, into: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 column sums of a 2-D bf16/f32 matrix (bias gradient).  ``into``: accumulate into this
+    fp32 [cols] buffer instead of returning a new one."""
     _req_cuda(a)
     rows, cols = a.shape
-    out = torch.empty(cols, dtype=torch.float32, device=a.device)
+    out = into if into is not None else torch.empty(cols, dtype=torch.float32, device=a.device)
     ws = torch.empty(L.lib().mb_colsum_workspace(rows, cols), dtype=torch.uint8, device=a.device)
     with _rec("colsum", float(rows * cols * a.element_size()), "byte", kernels=2):
         L.check(L.lib().mb_colsum(a.data_ptr(), L.MB_BF16 if a.dtype == torch.bfloat16 else L.MB_F32,
-                                  out.data_ptr(), 0, ws.data_ptr(), rows, cols, a.stride(0), _stream()),
+                                  out.data_ptr(), 1 if into is not None else 0, ws.data_ptr(), rows, cols,
+                                  a.stride(0), _stream()),
                 "mb_colsum")
     return out
 

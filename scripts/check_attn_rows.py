@@ -102,12 +102,19 @@ def group_rowops():
         ok &= report("   ln bwd dx(+dres)", dx, xr.grad + dres, tol=1e-4)
         ok &= report("   ln bwd dw", dw, wr.grad, tol=1e-4)
         ok &= report("   ln bwd db", db, br.grad, tol=1e-4)
-        dx2, _, _ = ops.layernorm_bwd(dy.bfloat16(), x, w, mean, rstd)
+        dx2, dx2b, _, _ = ops.layernorm_bwd(dy.bfloat16(), x, w, mean, rstd, want_bf16=True)
         ok &= report("   ln bwd dx (bf16 dy)", dx2, xr.grad, tol=1e-2)
-    a = torch.randn(5000, 768, device=dev)
-    ok &= report("colsum f32", ops.colsum(a)[None], a.sum(0)[None], tol=1e-4)
-    ab = a.bfloat16()
-    ok &= report("colsum bf16", ops.colsum(ab)[None], ab.float().sum(0)[None], tol=1e-4)
+        exact = torch.equal(dx2b, dx2.bfloat16())
+        print(f"[{'PASS' if exact else 'FAIL'}]    ln bwd bf16 twin == round(dx)", flush=True)
+        ok &= exact
+    for (rows, cols) in [(5000, 768), (25344, 1024), (25344, 3072), (65536, 256), (999, 832), (3, 8), (70, 104)]:
+        a = torch.randn(rows, cols, device=dev)
+        ok &= report(f"colsum f32 {rows}x{cols}", ops.colsum(a)[None], a.double().sum(0).float()[None], tol=1e-4)
+        ab = a.bfloat16()
+        ok &= report(f"colsum bf16 {rows}x{cols}", ops.colsum(ab)[None], ab.double().sum(0).float()[None], tol=1e-4)
+    big = torch.randn(4096, 3072, device=dev).bfloat16()
+    ok &= report("colsum bf16 column slice (ld 3072)", ops.colsum(big[:, 1024:2048])[None],
+                 big[:, 1024:2048].double().sum(0).float()[None], tol=1e-4)
     # gather / scatter: bit exact
     B, n_src, D, n_keep = 5, 768, 1024, 98
     src = torch.randn(B, n_src, D, device=dev)
@@ -179,6 +186,43 @@ def group_attnperf():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f"[PERF] layernorm 131328x1024 f32->bf16: {ms:.3f} ms = {x.numel() * 6 / ms / 1e6:.0f} GB/s", flush=True)
+    return True
+
+
+def _time(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def group_rowperf():
+    """HBM-bound row kernels at pretraining size (cfg 4: 256 x 99 token rows, D = 1024)."""
+    rows, D = 25344, 1024
+    x = torch.randn(rows, D, device=dev)
+    w, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    y, mean, rstd = ops.layernorm(x, w, b, save_stats=True)
+    dy = torch.randn(rows, D, device=dev).bfloat16()
+    dres = torch.randn(rows, D, device=dev)
+    ms = _time(lambda: ops.layernorm_bwd(dy, x, w, mean, rstd, dres=dres, want_bf16=True))
+    print(f"[PERF] layernorm_bwd {rows}x{D} (+dres, +bf16 twin): {ms * 1e3:.1f} us = "
+          f"{rows * D * 16 / ms / 1e6:.0f} GB/s", flush=True)
+    ms = _time(lambda: ops.layernorm(x, w, b, save_stats=True))
+    print(f"[PERF] layernorm_fwd {rows}x{D}: {ms * 1e3:.1f} us = {rows * D * 6 / ms / 1e6:.0f} GB/s", flush=True)
+    for cols in (1024, 3072, 4096):
+        a = torch.randn(rows, cols, device=dev).bfloat16()
+        ms = _time(lambda: ops.colsum(a))
+        print(f"[PERF] colsum bf16 {rows}x{cols}: {ms * 1e3:.1f} us = {rows * cols * 2 / ms / 1e6:.0f} GB/s",
+              flush=True)
+    a = torch.randn(65536, 256, device=dev).bfloat16()
+    ms = _time(lambda: ops.colsum(a))
+    print(f"[PERF] colsum bf16 65536x256: {ms * 1e3:.1f} us = {65536 * 256 * 2 / ms / 1e6:.0f} GB/s", flush=True)
     return True
 
 

@@ -94,3 +94,38 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
     with pytest.raises(_lib.MirageB200Error):
         _lib.lib()
+
+
+def test_grad_sink_matches_autograd():
+    """Gradients accumulated by the kernels straight into the all-reduce buckets (functional.set_grad_sink,
+    used by GradBucketAllReduce) equal the ones autograd materialises without a sink."""
+    from mirage_b200 import functional as Fn
+    from mirage_b200.ddp import GradBucketAllReduce
+    from pretrain_case import MODS, b200_step, build_criteria, build_pretrain_model, sample_masks
+    dev = torch.device("cuda:0")
+    model, _ = build_pretrain_model("tiny")
+    load_synth(model, seed=3)
+    model = model.to(dev).train()
+    crits = build_criteria()
+    x = {k: v.to(dev) for k, v in synth_images(3, MODS, seed=21).items()}
+    tm, keep, restore = sample_masks(model, 3, 98, seed=5)
+    masks = ({k: v.to(dev) for k, v in tm.items()}, keep.to(dev), restore.to(dev))
+    _, _, ref = b200_step(model, crits, x, masks)
+    ref = {k: v.detach().clone() for k, v in ref.items()}
+    try:
+        ddp = GradBucketAllReduce(model, bucket_mb=1.0)
+        assert Fn._grad_sink is ddp
+        for _ in range(2):  # twice: zero_grad must fully reset the buckets
+            ddp.zero_grad()
+            preds, m = model(x, num_encoded_tokens=98, alphas=1.0, sample_tasks_uniformly=False)
+            sum(crits[d](preds[d].float(), x[d], mask=m[d]) for d in MODS).backward()
+            ddp.finish()
+        assert all(b.pending == 0 for b in ddp.buckets), [b.pending for b in ddp.buckets]
+        for k, p in model.named_parameters():
+            if not p.requires_grad:
+                continue
+            a, b = p.grad.float().flatten(), ref[k].float().flatten()
+            tol = 1e-4 * (b.abs().max().item() + 1e-6) + 1e-6
+            assert (a - b).abs().max().item() <= tol, (k, (a - b).abs().max().item(), tol)
+    finally:
+        Fn.set_grad_sink(None)
