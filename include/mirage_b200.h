@@ -55,8 +55,10 @@ void mb_clear_tensor_map_cache(void);
  *
  * Epilogue, applied in this order on the fp32 accumulator acc[m, n]:
  *   1. if bias:            acc += bias[n]                                   (f32 [N])
- *   2. if MB_EPI_GELU:     (aux_out ? aux_out[m,n] = bf16(acc) : -);  acc = gelu_erf(acc)
- *   3. if MB_EPI_DGELU:    acc *= gelu_erf'(aux_in[m,n])                     (bf16 [M, ld_aux])
+ *   2. if MB_EPI_GELU:     (aux_out ? aux_out[m,n] = bf16(acc) : -);  acc = GELU(acc)
+ *   3. if MB_EPI_DGELU:    acc *= GELU'(aux_in[m,n])                         (bf16 [M, ld_aux])
+ *      GELU is nn.GELU()'s exact erf form evaluated through a tanh-form fit (max abs error 3e-5, derivative
+ *      1.2e-4; csrc/common.cuh gelu_fast2) -- below the bf16 rounding of the stored result.
  *   4. if residual:        acc += residual[(res_period ? m % res_period : m), n]   (f32, ld_res)
  *   5. store: out_dtype MB_BF16 or MB_F32 at out[r(m) * ldc + n];  with MB_EPI_ATOMIC (required
  *      when k_splits > 1) the store is an fp32 atomic add into a pre-zeroed (or accumulating) buffer.
