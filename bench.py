@@ -243,11 +243,9 @@ def run_gpu(args):
                 return model(dev_in)
 
         def step_e2e():
-            with torch.no_grad():
-                xin = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
-                out = model(xin)
-                host_out.copy_(out, non_blocking=True)
-            return out
+            # public host-to-host call: pinned inputs -> encoder -> pinned output, copies overlapped
+            # with compute chunk by chunk (mirage_hf.MIRAGEWrapper.encode_host)
+            return model.encode_host(host_in, out=host_out, chunk=args.e2e_chunk)
         h2d = sum(v.numel() * v.element_size() for v in host_in.values())
         d2h = host_out.numel() * host_out.element_size()
         flop_per_sample = GFLOP_FWD[args.workload] * 1e9
@@ -300,14 +298,17 @@ def run_gpu(args):
         ms_total, ms_e2e = t.tolist()
 
     # per-kernel roofline pass: one more step with CUDA events around every launch (rank 0)
+    # (every rank runs the step -- the pretraining step contains the gradient all-reduce -- but only
+    # rank 0 records)
     roofline = None
     kernels = None
+    kt = KernelTimer()
     if rank == 0:
-        kt = KernelTimer()
         ops.set_recorder(kt)
-        step()
-        torch.cuda.synchronize()
-        ops.set_recorder(None)
+    step()
+    torch.cuda.synchronize()
+    ops.set_recorder(None)
+    if rank == 0:
         agg = kt.summary()
         peaks = measured_peaks()
         tot = sum(a["ms"] for a in agg.values()) or 1.0
@@ -374,6 +375,7 @@ def main():
     ap.add_argument("--workload", default="encoder_large", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=64, help="images per pipelined chunk of the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

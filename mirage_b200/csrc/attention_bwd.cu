@@ -5,14 +5,20 @@
 //                dQ = dS K,  dK = dS^T Q,   D_i = rowsum(dO_i o O_i).
 // Backward of F.scaled_dot_product_attention at mirage/utils.py:181-185 / :216-220.
 //
-// One CTA per (batch, head).  Outer loop over key blocks j (128 keys), inner loop over query tiles i
-// (128 rows).  dK_j / dV_j accumulate in TMEM across the inner loop; dQ_i is produced per (j, i) and
-// (when there is more than one key block) accumulated in an fp32 workspace by the thread that owns
-// the row -- no atomics anywhere.
+// Persistent CTAs (one per SM) walk work items = (batch, head); inside an item the outer loop runs over
+// key blocks j (128 keys), the inner loop over query tiles i (128 rows).  dK_j / dV_j accumulate in
+// TMEM across the inner loop; dQ_i is produced per (j, i) and (when there is more than one key block)
+// accumulated in an fp32 workspace by the thread that owns the row -- no atomics anywhere.
+// The (j, i) iterations of ALL items form one software pipeline (the first version ran one CTA per
+// item with every stage serialised: 228 us for the 4096 (b, h) problems of cfg 4, 15k clk per item):
 //
-//   warp 0     TMA producer: K_j, V_j per key block; Q_i, dO_i per (j, i)
-//   warp 1     TMEM allocator + MMA issuer (one lane)
-//   warps 2-5  one thread per query row: P and dS (bf16) into 128B-swizzled smem, dQ/dK/dV write-out
+//   warp 0       TMA producer: K_j, V_j per key block (2 slots); Q_i, dO_i per iteration (2 slots)
+//   warp 1       MMA issuer (one lane):  MMA1(t+1) = {S, dP}  is issued as soon as the compute warps have
+//                copied S/dP(t) to registers, i.e. it overlaps the exponentials of iteration t and MMA2(t)
+//   warps 4-7    compute, key columns [0, 64)   of the tile: one thread per query row holds 64 S + 64 dP
+//   warps 8-11   compute, key columns [64, 128)  values, writes bf16 P and dS into 128B-swizzled smem
+//   warps 12-15  drain: dV / dK (end of a key block) and dQ (every iteration) TMEM -> global; the
+//                accumulators are handed back to the MMA warp right after the TMEM reads, before the stores
 //
 // The same swizzled P / dS tile is consumed twice: as a K-major A operand (dQ = dS K) and, through
 // the MN-major descriptor, as the transposed A operand (dV = P^T dO, dK = dS^T Q) -- no transposes.
@@ -37,21 +43,21 @@ struct AttnBwdDev {
   float scale, scale_log2;
 };
 
-constexpr int kAttnBwdThreads = 192;
+constexpr int kAttnBwdThreads = 512;
 
 template <int HD>
 struct AttnBwdCfg {
   static constexpr int kRowBytes = HD * 2;
   static constexpr int kTileBytes = 128 * kRowBytes;
   static constexpr int kPBytes = 128 * 128 * 2;
-  static constexpr int kOffK = 0;
-  static constexpr int kOffV = kOffK + kTileBytes;
-  static constexpr int kOffQ = kOffV + kTileBytes;
-  static constexpr int kOffDO = kOffQ + kTileBytes;
-  static constexpr int kOffP = kOffDO + kTileBytes;
+  static constexpr int kOffK = 0;                    // 2 slots each
+  static constexpr int kOffV = kOffK + 2 * kTileBytes;
+  static constexpr int kOffQ = kOffV + 2 * kTileBytes;
+  static constexpr int kOffDO = kOffQ + 2 * kTileBytes;
+  static constexpr int kOffP = kOffDO + 2 * kTileBytes;
   static constexpr int kOffDS = kOffP + kPBytes;
   static constexpr int kOffBar = kOffDS + kPBytes;
-  static constexpr int kSmemBytes = kOffBar + 128;
+  static constexpr int kSmemBytes = kOffBar + 256;
   static constexpr int kSwizzle = (HD == 64) ? 128 : 64;
 };
 
@@ -67,19 +73,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
-  uint64_t* kv_full = bars + 0;
-  uint64_t* kv_empty = bars + 1;
-  uint64_t* qdo_full = bars + 2;
-  uint64_t* qdo_empty = bars + 3;
-  uint64_t* sdp_full = bars + 4;
-  uint64_t* pds_full = bars + 5;
-  uint64_t* mma2_done = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* kv_full = bars + 0;    // 2  TMA tx
+  uint64_t* kv_empty = bars + 2;   // 2  MMA commit after the key block's last MMA2
+  uint64_t* qdo_full = bars + 4;   // 2  TMA tx
+  uint64_t* qdo_empty = bars + 6;  // 2  MMA commit after MMA2(t)
+  uint64_t* sdp_full = bars + 8;   // MMA commit: S, dP of iteration t complete
+  uint64_t* sdp_free = bars + 9;   // 256 compute threads: S, dP copied to registers
+  uint64_t* pds_full = bars + 10;  // 256 compute threads: P, dS tiles written
+  uint64_t* mma2_done = bars + 11; // MMA commit: dV, dK, dQ of iteration t complete, P/dS tiles free
+  uint64_t* acc_free = bars + 12;  // 128 drain threads: accumulators read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int h = blockIdx.x % p.H;
-  const int b = blockIdx.x / p.H;
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("mirage_b200: attention-bwd smem base not 1024-byte aligned\n");
@@ -90,13 +96,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_do);
-    mbar_init(kv_full, 1);
-    mbar_init(kv_empty, 1);
-    mbar_init(qdo_full, 1);
-    mbar_init(qdo_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&qdo_full[s], 1);
+      mbar_init(&qdo_empty[s], 1);
+    }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(sdp_free, 256);
+    mbar_init(pds_full, 256);
     mbar_init(mma2_done, 1);
+    mbar_init(acc_free, 128);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -108,174 +118,234 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int kvb = p.kv_blocks, qt = p.q_tiles;
+  const int n_items = p.B * p.H;
 
-  if (warp == 0 && lane == 0) {
-    // ---------------------------------------------------------------- TMA producer
-    int it = 0;
-    for (int j = 0; j < kvb; ++j) {
-      mbar_wait(kv_empty, (j & 1) ^ 1);
-      mbar_arrive_expect_tx(kv_full, 2 * Cfg::kTileBytes);
-      tma_load_3d(smem + Cfg::kOffK, &tm_k, kv_full, h * HD, j * 128, b);
-      tma_load_3d(smem + Cfg::kOffV, &tm_v, kv_full, h * HD, j * 128, b);
-      for (int i = 0; i < qt; ++i, ++it) {
-        mbar_wait(qdo_empty, (it & 1) ^ 1);
-        mbar_arrive_expect_tx(qdo_full, 2 * Cfg::kTileBytes);
-        tma_load_3d(smem + Cfg::kOffQ, &tm_q, qdo_full, h * HD, i * 128, b);
-        tma_load_3d(smem + Cfg::kOffDO, &tm_do, qdo_full, h * HD, i * 128, b);
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if (warp == 0 && lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      int t = 0, jb = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int h = item % p.H, b = item / p.H;
+        for (int j = 0; j < kvb; ++j, ++jb) {
+          const int ks = jb & 1;
+          mbar_wait(&kv_empty[ks], ((jb >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[ks], 2 * Cfg::kTileBytes);
+          tma_load_3d(smem + Cfg::kOffK + ks * Cfg::kTileBytes, &tm_k, &kv_full[ks], h * HD, j * 128, b);
+          tma_load_3d(smem + Cfg::kOffV + ks * Cfg::kTileBytes, &tm_v, &kv_full[ks], h * HD, j * 128, b);
+          for (int i = 0; i < qt; ++i, ++t) {
+            const int qs = t & 1;
+            mbar_wait(&qdo_empty[qs], ((t >> 1) & 1) ^ 1);
+            mbar_arrive_expect_tx(&qdo_full[qs], 2 * Cfg::kTileBytes);
+            tma_load_3d(smem + Cfg::kOffQ + qs * Cfg::kTileBytes, &tm_q, &qdo_full[qs], h * HD, i * 128, b);
+            tma_load_3d(smem + Cfg::kOffDO + qs * Cfg::kTileBytes, &tm_do, &qdo_full[qs], h * HD, i * 128, b);
+          }
+        }
       }
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ---------------------------------------------------------------- MMA issuer
-    const uint32_t k_addr = smem_u32(smem + Cfg::kOffK);
-    const uint32_t v_addr = smem_u32(smem + Cfg::kOffV);
-    const uint32_t q_addr = smem_u32(smem + Cfg::kOffQ);
-    const uint32_t do_addr = smem_u32(smem + Cfg::kOffDO);
-    const uint32_t p_addr = smem_u32(smem + Cfg::kOffP);
-    const uint32_t ds_addr = smem_u32(smem + Cfg::kOffDS);
-    constexpr uint32_t idesc_dkv = make_idesc(128, HD, kFmtBF16, 1, 1);
-    constexpr uint32_t idesc_dq = make_idesc(128, HD, kFmtBF16, 0, 1);
-    int it = 0;
-    for (int j = 0; j < kvb; ++j) {
-      const int valid = min(128, p.Nk - j * 128);
-      const uint32_t ncols = static_cast<uint32_t>((valid + 15) & ~15);
-      const uint32_t idesc_s = make_idesc(128, ncols, kFmtBF16, 0, 0);
-      mbar_wait(kv_full, j & 1);
-      for (int i = 0; i < qt; ++i, ++it) {
-        mbar_wait(qdo_full, it & 1);
+    } else if (warp == 1 && lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      const uint32_t k_addr0 = smem_u32(smem + Cfg::kOffK);
+      const uint32_t v_addr0 = smem_u32(smem + Cfg::kOffV);
+      const uint32_t q_addr0 = smem_u32(smem + Cfg::kOffQ);
+      const uint32_t do_addr0 = smem_u32(smem + Cfg::kOffDO);
+      const uint32_t p_addr = smem_u32(smem + Cfg::kOffP);
+      const uint32_t ds_addr = smem_u32(smem + Cfg::kOffDS);
+      constexpr uint32_t idesc_dkv = make_idesc(128, HD, kFmtBF16, 1, 1);
+      constexpr uint32_t idesc_dq = make_idesc(128, HD, kFmtBF16, 0, 1);
+      const int iters_per_item = kvb * qt;
+      const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int T = my_items * iters_per_item;
+
+      // MMA1(t): S = Q_i K_j^T ; dP = dO_i V_j^T   (K-major operands, N = ncols)
+      auto mma1 = [&](int t) {
+        const int within = t % iters_per_item;
+        const int j = within / qt, i = within - j * qt;
+        const int jb = (t / iters_per_item) * kvb + j;
+        const int valid = min(128, p.Nk - j * 128);
+        const uint32_t idesc_s = make_idesc(128, static_cast<uint32_t>((valid + 15) & ~15), kFmtBF16, 0, 0);
+        if (t > 0) mbar_wait(sdp_free, (t - 1) & 1);
+        if (i == 0) mbar_wait(&kv_full[jb & 1], (jb >> 1) & 1);
+        mbar_wait(&qdo_full[t & 1], (t >> 1) & 1);
         tc_fence_after();
-        // S = Q_i K_j^T ; dP = dO_i V_j^T      (K-major operands, N = ncols)
+        const uint32_t q_addr = q_addr0 + (t & 1) * Cfg::kTileBytes, do_addr = do_addr0 + (t & 1) * Cfg::kTileBytes;
+        const uint32_t k_addr = k_addr0 + (jb & 1) * Cfg::kTileBytes, v_addr = v_addr0 + (jb & 1) * Cfg::kTileBytes;
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
+        for (int k = 0; k < HD / 16; ++k)
           umma_f16_ss(tmem_base + 0, make_smem_desc(q_addr + k * 32, 0, kSbo, kSw),
                       make_smem_desc(k_addr + k * 32, 0, kSbo, kSw), idesc_s, k > 0 ? 1u : 0u);
-        }
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
+        for (int k = 0; k < HD / 16; ++k)
           umma_f16_ss(tmem_base + 128, make_smem_desc(do_addr + k * 32, 0, kSbo, kSw),
                       make_smem_desc(v_addr + k * 32, 0, kSbo, kSw), idesc_s, k > 0 ? 1u : 0u);
-        }
         umma_commit(sdp_full);
+      };
 
-        mbar_wait(pds_full, it & 1);
+      if (T > 0) mma1(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) mma1(t + 1);
+        const int within = t % iters_per_item;
+        const int j = within / qt, i = within - j * qt;
+        const int jb = (t / iters_per_item) * kvb + j;
+        const int valid = min(128, p.Nk - j * 128);
+        const uint32_t q_addr = q_addr0 + (t & 1) * Cfg::kTileBytes, do_addr = do_addr0 + (t & 1) * Cfg::kTileBytes;
+        const uint32_t k_addr = k_addr0 + (jb & 1) * Cfg::kTileBytes;
+        mbar_wait(pds_full, t & 1);
+        if (t > 0) mbar_wait(acc_free, (t - 1) & 1);
         tc_fence_after();
         // dV_j += P^T dO_i ; dK_j += dS^T Q_i   (A = P / dS read MN-major: M = keys, K = query rows)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < 8; ++kk)
           umma_f16_ss(tmem_base + 256, make_smem_desc(p_addr + kk * 2048, 16384, 1024),
                       make_smem_desc(do_addr + kk * kRowStep16, 0, kSbo, kSw), idesc_dkv,
                       (i > 0 || kk > 0) ? 1u : 0u);
-        }
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < 8; ++kk)
           umma_f16_ss(tmem_base + 320, make_smem_desc(ds_addr + kk * 2048, 16384, 1024),
                       make_smem_desc(q_addr + kk * kRowStep16, 0, kSbo, kSw), idesc_dkv,
                       (i > 0 || kk > 0) ? 1u : 0u);
-        }
         // dQ_i(j) = dS K_j                      (A = dS K-major: M = query rows, K = keys)
         const int ksteps = (valid + 15) >> 4;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          umma_f16_ss(tmem_base + 384,
-                      make_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
-                      make_smem_desc(k_addr + kk * kRowStep16, 0, kSbo, kSw), idesc_dq,
-                      kk > 0 ? 1u : 0u);
-        }
+        for (int kk = 0; kk < ksteps; ++kk)
+          umma_f16_ss(tmem_base + 384, make_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+                      make_smem_desc(k_addr + kk * kRowStep16, 0, kSbo, kSw), idesc_dq, kk > 0 ? 1u : 0u);
         umma_commit(mma2_done);
-        umma_commit(qdo_empty);
-        if (i == qt - 1) umma_commit(kv_empty);
+        umma_commit(&qdo_empty[t & 1]);
+        if (i == qt - 1) umma_commit(&kv_empty[jb & 1]);
       }
     }
-  } else if (warp >= 2) {
+  } else if (warp < 12) {
     // ---------------------------------------------------------------- compute warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    const int half = (warp - 4) >> 2;  // which 64 key columns of the tile
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    uint8_t* p_row = smem + Cfg::kOffP + r * 128;
-    uint8_t* ds_row = smem + Cfg::kOffDS + r * 128;
+    uint8_t* p_row = smem + Cfg::kOffP + half * 16384 + r * 128;
+    uint8_t* ds_row = smem + Cfg::kOffDS + half * 16384 + r * 128;
     const float log2e = 1.4426950408889634f;
-    int it = 0;
-    for (int j = 0; j < kvb; ++j) {
-      const int valid = min(128, p.Nk - j * 128);
-      for (int i = 0; i < qt; ++i, ++it) {
-        const int qrow = i * 128 + r;
-        const bool row_ok = qrow < p.Nq;
-        // per-row statistics: LSE and D = <dO, O>
-        float lse2 = 0.f, dsum = 0.f;
-        if (row_ok) {
-          lse2 = p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qrow] * log2e;
-          const __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Nq + qrow) * p.ldo + h * HD;
-          const __nv_bfloat16* drow = p.d_o + (static_cast<long long>(b) * p.Nq + qrow) * p.lddo + h * HD;
+    int t = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int h = item % p.H, b = item / p.H;
+      for (int j = 0; j < kvb; ++j) {
+        const int valid = min(128, p.Nk - j * 128) - half * 64;  // valid columns of this half (may be <= 0)
+        for (int i = 0; i < qt; ++i, ++t) {
+          const int qrow = i * 128 + r;
+          // per-row statistics: LSE and D = <dO, O>  (rows past Nq: Q/dO tiles are zero-filled, any
+          // finite value keeps their P/dS harmless)
+          float lse2 = 0.f, dsum = 0.f;
+          if (qrow < p.Nq) {
+            lse2 = p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qrow] * log2e;
+            const __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Nq + qrow) * p.ldo + h * HD;
+            const __nv_bfloat16* drow = p.d_o + (static_cast<long long>(b) * p.Nq + qrow) * p.lddo + h * HD;
 #pragma unroll
-          for (int c = 0; c < HD / 8; ++c) {
-            const uint4 a = *reinterpret_cast<const uint4*>(orow + c * 8);
-            const uint4 g = *reinterpret_cast<const uint4*>(drow + c * 8);
-            const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z),
-                         a3 = unpack_bf16x2(a.w);
-            const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z),
-                         g3 = unpack_bf16x2(g.w);
-            dsum += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y +
-                    a3.x * g3.x + a3.y * g3.y;
-          }
-        }
-        mbar_wait(sdp_full, it & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t vs[32], vd[32];
-          if (c * 32 < valid) {  // warp-uniform
-            tmem_ld_32x32b_x32(tmem_base + lane_off + c * 32, vs);
-            tmem_ld_32x32b_x32(tmem_base + lane_off + 128 + c * 32, vd);
-            tmem_ld_wait();
-          }
-          uint8_t* pd = p_row + (c >> 1) * 16384;
-          uint8_t* dd = ds_row + (c >> 1) * 16384;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float pv[8], dv_[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int col = c * 32 + t * 8 + e;
-              float pe = 0.f, de = 0.f;
-              if (row_ok && col < valid) {
-                pe = fast_exp2(fmaf(__uint_as_float(vs[t * 8 + e]), p.scale_log2, -lse2));
-                de = pe * (__uint_as_float(vd[t * 8 + e]) - dsum) * p.scale;
-              }
-              pv[e] = pe;
-              dv_[e] = de;
+            for (int c = 0; c < HD / 8; ++c) {
+              const uint4 a = *reinterpret_cast<const uint4*>(orow + c * 8);
+              const uint4 g = *reinterpret_cast<const uint4*>(drow + c * 8);
+              const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z),
+                           a3 = unpack_bf16x2(a.w);
+              const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z),
+                           g3 = unpack_bf16x2(g.w);
+              dsum += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y +
+                      a3.x * g3.x + a3.y * g3.y;
             }
-            uint4 pk, dk4;
-            pk.x = pack_bf16x2(pv[0], pv[1]);
-            pk.y = pack_bf16x2(pv[2], pv[3]);
-            pk.z = pack_bf16x2(pv[4], pv[5]);
-            pk.w = pack_bf16x2(pv[6], pv[7]);
-            dk4.x = pack_bf16x2(dv_[0], dv_[1]);
-            dk4.y = pack_bf16x2(dv_[2], dv_[3]);
-            dk4.z = pack_bf16x2(dv_[4], dv_[5]);
-            dk4.w = pack_bf16x2(dv_[6], dv_[7]);
-            const uint32_t c8 = static_cast<uint32_t>((c & 1) * 4 + t);
-            *reinterpret_cast<uint4*>(pd + ((c8 ^ sw) << 4)) = pk;
-            *reinterpret_cast<uint4*>(dd + ((c8 ^ sw) << 4)) = dk4;
           }
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        mbar_arrive(pds_full);
-
-        // dQ_i (+)= dS K_j
-        mbar_wait(mma2_done, it & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_off + 384 + c * 32, v);
+          mbar_wait(sdp_full, t & 1);
+          tc_fence_after();
+          uint32_t vs[64], vd[64];
+          tmem_ld_32x32b_x32_p(tmem_base + lane_off + half * 64, vs);
+          tmem_ld_32x32b_x32_p(tmem_base + lane_off + half * 64 + 32, vs + 32);
+          tmem_ld_32x32b_x32_p(tmem_base + lane_off + 128 + half * 64, vd);
+          tmem_ld_32x32b_x32_p(tmem_base + lane_off + 128 + half * 64 + 32, vd + 32);
           tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(sdp_free);  // MMA1(t+1) may overwrite S / dP now
+          // P and dS in place: vs[e/2] <- packed P pair, vd[e/2] <- packed dS pair
+          const float neg_lse = -lse2;
+          const float ds_scale = p.scale;
+#pragma unroll
+          for (int e = 0; e < 64; e += 2) {
+            const float x0 = fmaf(__uint_as_float(vs[e]), p.scale_log2, neg_lse);
+            const float x1 = fmaf(__uint_as_float(vs[e + 1]), p.scale_log2, neg_lse);
+            float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+            float d0 = p0 * (__uint_as_float(vd[e]) - dsum) * ds_scale;
+            float d1 = p1 * (__uint_as_float(vd[e + 1]) - dsum) * ds_scale;
+            if (valid < 64) {  // ragged key block: masked keys get P = dS = 0 (their S / dP columns were
+                               // never written by the MMA and may hold anything, NaN included)
+              if (e >= valid) p0 = d0 = 0.f;
+              if (e + 1 >= valid) p1 = d1 = 0.f;
+            }
+            vs[e >> 1] = pack_bf16x2(p0, p1);
+            vd[e >> 1] = pack_bf16x2(d0, d1);
+          }
+          if (t > 0) mbar_wait(mma2_done, (t - 1) & 1);  // MMA2(t-1) has finished reading the P / dS tiles
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint32_t off = (static_cast<uint32_t>(c8) ^ sw) << 4;
+            *reinterpret_cast<uint4*>(p_row + off) = make_uint4(vs[c8 * 4], vs[c8 * 4 + 1], vs[c8 * 4 + 2], vs[c8 * 4 + 3]);
+            *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(vd[c8 * 4], vd[c8 * 4 + 1], vd[c8 * 4 + 2], vd[c8 * 4 + 3]);
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(pds_full);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- drain warps
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    int t = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int h = item % p.H, b = item / p.H;
+      for (int j = 0; j < kvb; ++j) {
+        const int krow = j * 128 + r;
+        for (int i = 0; i < qt; ++i, ++t) {
+          const int qrow = i * 128 + r;
+          const bool row_ok = qrow < p.Nq;
+          mbar_wait(mma2_done, t & 1);
+          tc_fence_after();
+          if (i == qt - 1) {
+            // dV_j, dK_j complete: TMEM -> bf16 -> global (stores are fire-and-forget)
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+              __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
+              const long long ld = which == 0 ? p.lddv : p.lddk;
+              __nv_bfloat16* dst = base + (static_cast<long long>(b) * p.Nk + krow) * ld + h * HD;
+#pragma unroll
+              for (int c = 0; c < HD / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + lane_off + 256 + which * 64 + c * 32, v);
+                tmem_ld_wait();
+                if (krow < p.Nk) {
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4) {
+                    uint4 pk;
+                    pk.x = pack_bf16x2(__uint_as_float(v[q4 * 8 + 0]), __uint_as_float(v[q4 * 8 + 1]));
+                    pk.y = pack_bf16x2(__uint_as_float(v[q4 * 8 + 2]), __uint_as_float(v[q4 * 8 + 3]));
+                    pk.z = pack_bf16x2(__uint_as_float(v[q4 * 8 + 4]), __uint_as_float(v[q4 * 8 + 5]));
+                    pk.w = pack_bf16x2(__uint_as_float(v[q4 * 8 + 6]), __uint_as_float(v[q4 * 8 + 7]));
+                    *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = pk;
+                  }
+                }
+              }
+            }
+          }
+          // dQ_i(j): all TMEM reads first, then release the accumulators, then the global traffic
+          uint32_t v[HD];
+#pragma unroll
+          for (int c = 0; c < HD / 32; ++c) tmem_ld_32x32b_x32_p(tmem_base + lane_off + 384 + c * 32, v + c * 32);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(acc_free);
           if (row_ok) {
             const long long grow = static_cast<long long>(b) * p.Nq + qrow;
             if (kvb > 1) {
-              float* acc = p.dq_acc + grow * (static_cast<long long>(p.H) * HD) + h * HD + c * 32;
+              float* acc = p.dq_acc + grow * (static_cast<long long>(p.H) * HD) + h * HD;
               if (j > 0) {
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) {
+                for (int e = 0; e < HD; e += 4) {
                   const float4 a = *reinterpret_cast<const float4*>(acc + e);
                   v[e + 0] = __float_as_uint(__uint_as_float(v[e + 0]) + a.x);
                   v[e + 1] = __float_as_uint(__uint_as_float(v[e + 1]) + a.y);
@@ -285,53 +355,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               }
               if (j < kvb - 1) {
 #pragma unroll
-                for (int e = 0; e < 32; e += 4)
+                for (int e = 0; e < HD; e += 4)
                   *reinterpret_cast<float4*>(acc + e) =
-                      make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                  __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+                      make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                                  __uint_as_float(v[e + 3]));
               }
             }
             if (j == kvb - 1) {
-              __nv_bfloat16* dst = p.dq + grow * p.lddq + h * HD + c * 32;
+              __nv_bfloat16* dst = p.dq + grow * p.lddq + h * HD;
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
+              for (int q4 = 0; q4 < HD / 8; ++q4) {
                 uint4 pk;
-                pk.x = pack_bf16x2(__uint_as_float(v[t * 8 + 0]), __uint_as_float(v[t * 8 + 1]));
-                pk.y = pack_bf16x2(__uint_as_float(v[t * 8 + 2]), __uint_as_float(v[t * 8 + 3]));
-                pk.z = pack_bf16x2(__uint_as_float(v[t * 8 + 4]), __uint_as_float(v[t * 8 + 5]));
-                pk.w = pack_bf16x2(__uint_as_float(v[t * 8 + 6]), __uint_as_float(v[t * 8 + 7]));
-                *reinterpret_cast<uint4*>(dst + t * 8) = pk;
+                pk.x = pack_bf16x2(__uint_as_float(v[q4 * 8 + 0]), __uint_as_float(v[q4 * 8 + 1]));
+                pk.y = pack_bf16x2(__uint_as_float(v[q4 * 8 + 2]), __uint_as_float(v[q4 * 8 + 3]));
+                pk.z = pack_bf16x2(__uint_as_float(v[q4 * 8 + 4]), __uint_as_float(v[q4 * 8 + 5]));
+                pk.w = pack_bf16x2(__uint_as_float(v[q4 * 8 + 6]), __uint_as_float(v[q4 * 8 + 7]));
+                *reinterpret_cast<uint4*>(dst + q4 * 8) = pk;
               }
             }
           }
         }
       }
-      // dK_j, dV_j complete (the last mma2_done of this key block has been waited on above)
-      const int krow = j * 128 + r;
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
-        const long long ld = which == 0 ? p.lddv : p.lddk;
-#pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_off + 256 + which * 64 + c * 32, v);
-          tmem_ld_wait();
-          if (krow < p.Nk) {
-            __nv_bfloat16* dst = base + (static_cast<long long>(b) * p.Nk + krow) * ld + h * HD + c * 32;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              uint4 pk;
-              pk.x = pack_bf16x2(__uint_as_float(v[t * 8 + 0]), __uint_as_float(v[t * 8 + 1]));
-              pk.y = pack_bf16x2(__uint_as_float(v[t * 8 + 2]), __uint_as_float(v[t * 8 + 3]));
-              pk.z = pack_bf16x2(__uint_as_float(v[t * 8 + 4]), __uint_as_float(v[t * 8 + 5]));
-              pk.w = pack_bf16x2(__uint_as_float(v[t * 8 + 6]), __uint_as_float(v[t * 8 + 7]));
-              *reinterpret_cast<uint4*>(dst + t * 8) = pk;
-            }
-          }
-        }
-      }
-      tc_fence_before();
     }
   }
 
@@ -390,7 +434,8 @@ static int launch_attn_bwd(const mb_attn_bwd_args* a, cudaStream_t stream) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const long long grid = (long long)p.B * p.H;
+  const long long items = (long long)p.B * p.H;
+  const long long grid = items < sm_count() ? items : sm_count();  // persistent CTAs
   kern<<<(unsigned)grid, kAttnBwdThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, tdo, p);
   MB_CHECK_CUDA(cudaGetLastError());
   return 0;

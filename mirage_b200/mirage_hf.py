@@ -65,6 +65,61 @@ class MIRAGEWrapper(nn.Module):
         """x: {modality: [B, 1, H, W] in [0, 1]} -> encoder tokens [B, N_all + 1, D]."""
         return self.model(x)
 
+    @torch.no_grad()
+    def encode_host(self, x: dict, out: torch.Tensor | None = None, chunk: int = 64) -> torch.Tensor:
+        """Batch inference from HOST tensors to a HOST tensor with the copies hidden behind compute.
+
+        x: {modality: pinned CPU [B, 1, H, W]}; out: pinned CPU [B, N_all + 1, D] fp32 (allocated when
+        None).  The batch is walked in chunks on three streams -- H2D of chunk i+1, the encoder on chunk
+        i, D2H of chunk i-1 -- with double-buffered device staging, so a step costs the encoder time
+        plus one chunk of PCIe traffic instead of the whole batch's (new: the reference wrapper is a plain
+        ``.to(device)`` + forward, hf/mirage_hf.py:670-680).  Returns ``out`` once everything is enqueued;
+        the caller synchronises (``torch.cuda.current_stream().synchronize()``) before reading it.
+        """
+        dev = self.device
+        names = list(x.keys())
+        B = x[names[0]].shape[0]
+        chunk = max(1, min(chunk, B))
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_pipe_streams"):
+            self._pipe_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._pipe_streams
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        n_chunks = (B + chunk - 1) // chunk
+        staged, ev_in, ev_free = [None, None], [None, None], [None, None]
+        outs, ev_done = [None, None], [None, None]
+
+        def load(i):
+            b0, b1 = i * chunk, min(B, (i + 1) * chunk)
+            slot = i & 1
+            with torch.cuda.stream(s_in):
+                if ev_free[slot] is not None:
+                    s_in.wait_event(ev_free[slot])   # the encoder is done reading this staging slot
+                staged[slot] = {k: x[k][b0:b1].to(dev, non_blocking=True) for k in names}
+                ev_in[slot] = s_in.record_event()
+
+        load(0)
+        for i in range(n_chunks):
+            slot = i & 1
+            if i + 1 < n_chunks:
+                load(i + 1)
+            main.wait_event(ev_in[slot])
+            tok = self.model(staged[slot])
+            for t in staged[slot].values():
+                t.record_stream(main)
+            ev_free[slot] = main.record_event()
+            ev_tok = main.record_event()
+            if out is None:
+                out = torch.empty((B,) + tuple(tok.shape[1:]), dtype=tok.dtype).pin_memory()
+            b0, b1 = i * chunk, min(B, (i + 1) * chunk)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_tok)
+                out[b0:b1].copy_(tok, non_blocking=True)
+                tok.record_stream(s_out)
+        main.wait_stream(s_out)
+        return out
+
     def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True, assign: bool = False):
         return self.model.load_state_dict(state_dict, strict, assign)
 

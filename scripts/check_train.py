@@ -69,7 +69,41 @@ def group_attnbwd():
     ok &= attn_bwd_case(1, 1, 128, 128, 32)
     ok &= attn_bwd_case(2, 8, 256, 256, 32)
     ok &= attn_bwd_case(2, 8, 256, 99, 32, self_attn=False)
+    # many items per persistent CTA: the cross-item software pipeline (phases, slot reuse)
+    junk = torch.full((1 << 27,), float("nan"), device=dev)  # poison recycled memory
+    del junk
+    ok &= attn_bwd_case(40, 16, 99, 99, 64)
+    ok &= attn_bwd_case(12, 16, 257, 257, 64)
+    ok &= attn_bwd_case(48, 8, 256, 99, 32, self_attn=False)
+    ok &= attn_bwd_case(40, 8, 256, 256, 32)
+    ok &= attn_bwd_case(3, 50, 130, 70, 64, self_attn=False)
     return ok
+
+
+def group_attnbwdperf():
+    for (B, H, nq, nk, hd) in [(256, 16, 99, 99, 64), (256, 8, 256, 99, 32), (256, 8, 256, 256, 32), (64, 16, 257, 257, 64)]:
+        D = H * hd
+        q = torch.randn(B * nq, D, device=dev).bfloat16()
+        kv = torch.randn(B * nk, 2 * D, device=dev).bfloat16()
+        k, v = kv[:, :D], kv[:, D:]
+        lse = torch.empty(B, H, nq, device=dev)
+        o = ops.attention(q, k, v, batch=B, heads=H, nq=nq, nk=nk, head_dim=hd, scale=hd ** -0.5, lse=lse)
+        do = torch.randn(B * nq, D, device=dev).bfloat16()
+        dq, dk, dv = torch.empty_like(q), torch.empty(B * nk, D, dtype=torch.bfloat16, device=dev), torch.empty(B * nk, D, dtype=torch.bfloat16, device=dev)
+        fn = lambda: ops.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, batch=B, heads=H, nq=nq, nk=nk, head_dim=hd, scale=hd ** -0.5)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"[PERF] attn_bwd B={B} H={H} nq={nq} nk={nk} hd={hd}: {ms * 1e3:.1f} us = "
+              f"{10.0 * B * H * nq * nk * hd / ms / 1e9:.0f} TFLOP/s", flush=True)
+    return True
 
 
 def group_adapters():
