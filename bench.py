@@ -238,9 +238,10 @@ def run_gpu(args):
         D = model.model.dim_tokens
         host_out = torch.empty((per_gpu, n_tok, D), dtype=torch.float32).pin_memory()
 
-        def step():
+        def step_eager():
             with torch.no_grad():
                 return model(dev_in)
+        step = step_eager
 
         def step_e2e():
             # public host-to-host call: pinned inputs -> encoder -> pinned output, copies overlapped
@@ -252,7 +253,8 @@ def run_gpu(args):
         unit = "images/s"
     else:
         from bench_support import build_pretrain_step
-        step, step_e2e, h2d, d2h = build_pretrain_step(size, mods, per_gpu, dev, rank, world)
+        step, step_e2e, h2d, d2h, graph_hooks = build_pretrain_step(size, mods, per_gpu, dev, rank, world)
+        step_eager = step
         flop_per_sample = 3.0 * GFLOP_FWD[args.workload] * 1e9
         unit = "samples/s"
 
@@ -261,6 +263,25 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    # whole-step CUDA graph (falls back to eager launches when capture is not possible)
+    graphed = False
+    if args.graph:
+        try:
+            if kind == "encoder":
+                from mirage_b200.graphs import GraphedCallable
+                gstep = GraphedCallable(step_eager).capture()
+                step = gstep
+                graphed = True
+            elif world == 1:
+                step, step_e2e = graph_hooks()
+                graphed = True
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"bench.py: CUDA-graph capture failed ({type(e).__name__}: {e}); eager launches",
+                      file=sys.stderr, flush=True)
+            torch.cuda.synchronize()
+            step = step_eager
 
     W, K = max(3, args.warmup), max(1, args.steps)
     for _ in range(W):
@@ -278,7 +299,6 @@ def run_gpu(args):
     e1.record()
     sync_all()
     ms_total = e0.elapsed_time(e1)
-    launches = ops.launch_count()
     clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end through the public API with host buffers (H2D + D2H inside the timed region)
@@ -305,9 +325,13 @@ def run_gpu(args):
     kt = KernelTimer()
     if rank == 0:
         ops.set_recorder(kt)
-    step()
+    ops.reset_launch_count()
+    step_eager()
     torch.cuda.synchronize()
     ops.set_recorder(None)
+    # kernels of libmirage_b200.so launched inside the timed region: counted on one eager step (a graph
+    # replay launches the same kernels without passing through the Python counter) times K
+    launches = ops.launch_count() * K
     if rank == 0:
         agg = kt.summary()
         peaks = measured_peaks()
@@ -318,18 +342,24 @@ def run_gpu(args):
                    for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
         top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         name, a = top
+        traffic = None
+        try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture, if any
+            tr = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+            traffic = tr.get(args.workload, {}).get(name, {}).get("bytes_per_launch")
+        except Exception:
+            traffic = None
         if a["unit"] == "flop":
             ach = a["work"] / a["ms"] / 1e9
             peak = peaks["bf16_tflops_sustained"]
             roofline = {"kernel": name, "bound": "tensor", "achieved": round(ach, 1), "peak": peak,
-                        "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
+                        "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
                         "peak_source": peaks["source"] + " (sustained bf16)",
                         "per_launch": {"flops": a["work"] / a["launches"], "ms": a["ms"] / a["launches"]}}
         else:
             ach = a["work"] / a["ms"] / 1e6
             peak = peaks["hbm_gbs"]
             roofline = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak,
-                        "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                        "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
                         "peak_source": peaks["source"],
                         "per_launch": {"bytes": a["work"] / a["launches"], "ms": a["ms"] / a["launches"]}}
 
@@ -351,7 +381,8 @@ def run_gpu(args):
                        "per_gpu_batch": per_gpu, "global_batch": per_gpu * world,
                        "parallelism": f"dp{world} (batch-sharded, no collective)" if kind == "encoder"
                        else f"dp{world} (NCCL gradient all-reduce)",
-                       "l2_policy": "inputs_exceed_l2 (activations >> 126 MB per step)"},
+                       "l2_policy": "inputs_exceed_l2 (activations >> 126 MB per step)",
+                       "cuda_graph": graphed},
             "model_tflops": round(value * flop_per_sample / 1e12, 1),
             "model_frac_of_bf16_peak": round(value * flop_per_sample / 1e12 / world / peaks["bf16_tflops"], 4),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
@@ -375,6 +406,7 @@ def main():
     ap.add_argument("--workload", default="encoder_large", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel eagerly")
     ap.add_argument("--e2e-chunk", type=int, default=64, help="images per pipelined chunk of the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":

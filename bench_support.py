@@ -28,7 +28,7 @@ def build_pretrain_step(size, mods, per_gpu, dev, rank, world):
             continue
         (no_decay if (p.ndim <= 1 or n.endswith(".bias") or n in skip) else decay).append(p)
     opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}],
-                            lr=1e-4 * per_gpu * world / 256, betas=(0.9, 0.95), fused=True)
+                            lr=1e-4 * per_gpu * world / 256, betas=(0.9, 0.95), fused=True, capturable=True)
 
     base = synth_images(8, mods, seed=1234 + rank)
     reps = per_gpu // 8 + 1
@@ -55,8 +55,42 @@ def build_pretrain_step(size, mods, per_gpu, dev, rank, world):
         host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
 
+    def graph_hooks():
+        """Whole-step CUDA graph (single rank): forward + losses + backward + AdamW are captured once;
+        the token masks are sampled eagerly every step exactly as the reference does (CPU Dirichlet +
+        device noise, mirage/model.py:168-239) and copied into the fixed tensors the graph reads."""
+        from mirage_b200.graphs import GraphedCallable
+        sampler = model.generate_random_masks
+        toks = {d: torch.empty(per_gpu, 256, 0, device=dev) for d in mods}
+        tm0, keep0, restore0 = sampler(toks, 98, alphas=1.0)
+        fixed = ({d: t.clone() for d, t in tm0.items()}, keep0.clone(), restore0.clone())
+        x_fixed = {k: v.clone() for k, v in dev_in.items()}
+
+        def resample():
+            tm, keep, restore = sampler(toks, 98, alphas=1.0)
+            for d in mods:
+                fixed[0][d].copy_(tm[d])
+            fixed[1].copy_(keep)
+            fixed[2].copy_(restore)
+
+        model.generate_random_masks = lambda *a, **k: fixed
+        g = GraphedCallable(lambda: one_step(x_fixed)).capture()
+
+        def gstep():
+            resample()
+            return g()
+
+        def gstep_e2e():
+            for k in x_fixed:
+                x_fixed[k].copy_(host_in[k], non_blocking=True)
+            resample()
+            loss = g()
+            host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+            return loss
+        return gstep, gstep_e2e
+
     h2d = sum(v.numel() * v.element_size() for v in host_in.values())
-    return step, step_e2e, h2d, 4
+    return step, step_e2e, h2d, 4, graph_hooks
 
 
 def build_pretrain_oracle(size, mods, batch, seed):

@@ -40,6 +40,8 @@ class GradBucketAllReduce:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.average = average
+        # ncclAvg exists only in NCCL; other backends (gloo in the tests) sum and divide afterwards
+        self._nccl = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
         params = [p for p in module.parameters() if p.requires_grad]
         assert params, "no trainable parameters"
         # gradients become ready roughly in reverse registration order (output side first)
@@ -55,6 +57,7 @@ class GradBucketAllReduce:
             size += p.numel()
         self.buckets: List[_Bucket] = []
         self._owner = {}
+        self._reported = set()
         for g in groups:
             n = sum(p.numel() for p in g)
             flat = torch.zeros(n, dtype=torch.float32, device=g[0].device)
@@ -87,6 +90,12 @@ class GradBucketAllReduce:
 
     # -- hooks -----------------------------------------------------------------------------------
     def _on_grad_ready(self, p: torch.Tensor):
+        # reached from the post-accumulate hook and/or from the gradient sink's done(): depending on the
+        # PyTorch version the hook also fires for a parameter whose autograd node returned None (2.11
+        # does), so every parameter is counted at most once per step
+        if p in self._reported:
+            return
+        self._reported.add(p)
         b = self._owner[p]
         b.pending -= 1
         if b.pending == 0:
@@ -94,12 +103,13 @@ class GradBucketAllReduce:
 
     def _launch(self, b: _Bucket):
         if self.world > 1:
-            op = dist.ReduceOp.AVG if (self.average and b.flat.is_cuda) else dist.ReduceOp.SUM
+            op = dist.ReduceOp.AVG if (self.average and self._nccl) else dist.ReduceOp.SUM
             b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
 
     # -- step protocol -----------------------------------------------------------------------------
     def zero_grad(self):
         """Zero the buckets in place (keeps ``param.grad`` as views; never set grads to None)."""
+        self._reported.clear()
         for b in self.buckets:
             b.flat.zero_()
             b.pending = len(b.params)
@@ -119,7 +129,7 @@ class GradBucketAllReduce:
         for b in self.buckets:
             if b.work is not None:
                 b.work.wait()
-                if self.average and not b.flat.is_cuda:
+                if self.average and not self._nccl:
                     b.flat.div_(self.world)
                 b.work = None
 
