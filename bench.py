@@ -24,7 +24,8 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 # algorithmic FLOPs per sample (forward), SURVEY.md section 8(d) / BASELINE.md section 4
-GFLOP_FWD = {"encoder_base": 97.65, "encoder_large": 336.79, "pretrain_base": 24.07, "pretrain_large": 68.49}
+GFLOP_FWD = {"encoder_base": 97.65, "encoder_large": 336.79, "pretrain_base": 24.07, "pretrain_large": 68.49,
+             "cls_large": 162.25}
 
 WORKLOADS = {
     # name: (size, modalities, per-GPU batch, kind)
@@ -32,6 +33,7 @@ WORKLOADS = {
     "encoder_base": ("base", ["bscan", "slo"], 256, "encoder"),
     "pretrain_large": ("large", ["bscan", "slo", "bscanlayermap"], 256, "pretrain"),
     "pretrain_base": ("base", ["bscan", "slo", "bscanlayermap"], 256, "pretrain"),
+    "cls_large": ("large", ["bscan"], 64, "cls"),   # BASELINE configs[4]: fine-tune fwd+bwd, 64 per GPU
 }
 
 
@@ -126,6 +128,9 @@ def cpu_oracle_throughput(workload: str, budget_s: float = 20.0, batch: int = 2,
         def run():
             with torch.no_grad():
                 return O.light_forward(x, sd, depth, heads)
+    elif kind == "cls":
+        from bench_support import build_cls_oracle
+        run = build_cls_oracle(size, batch, seed)
     else:
         from bench_support import build_pretrain_oracle
         run = build_pretrain_oracle(size, mods, batch, seed)
@@ -251,6 +256,13 @@ def run_gpu(args):
         d2h = host_out.numel() * host_out.element_size()
         flop_per_sample = GFLOP_FWD[args.workload] * 1e9
         unit = "images/s"
+    elif kind == "cls":
+        from bench_support import build_cls_step
+        step, step_e2e, h2d, d2h = build_cls_step(size, per_gpu, dev, rank, world)
+        step_eager = step
+        graph_hooks = None
+        flop_per_sample = 3.0 * GFLOP_FWD[args.workload] * 1e9
+        unit = "samples/s"
     else:
         from bench_support import build_pretrain_step
         step, step_e2e, h2d, d2h, graph_hooks = build_pretrain_step(size, mods, per_gpu, dev, rank, world)
@@ -273,7 +285,7 @@ def run_gpu(args):
                 gstep = GraphedCallable(step_eager).capture()
                 step = gstep
                 graphed = True
-            elif world == 1:
+            elif world == 1 and graph_hooks is not None:
                 step, step_e2e = graph_hooks()
                 graphed = True
         except Exception as e:  # noqa: BLE001

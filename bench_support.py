@@ -93,6 +93,63 @@ def build_pretrain_step(size, mods, per_gpu, dev, rank, world):
     return step, step_e2e, h2d, 4, graph_hooks
 
 
+def build_cls_step(size, per_gpu, dev, rank, world):
+    """cfg 5: miragecls_factory['global'] full fine-tune step (forward + CE + backward + gradient
+    exchange + AdamW), bscan 512x512, 5 classes."""
+    from cls_case import build_cls_model
+    from helpers import synth_images
+    from mirage_b200.ddp import GradBucketAllReduce
+    model, _ = build_cls_model("global", 21, device=dev, size=size)
+    model.train()
+    ddp = GradBucketAllReduce(model, bucket_mb=64)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.05,
+                            fused=True)
+    base = synth_images(8, ["bscan"], seed=1234 + rank)["bscan"]
+    host_x = base.repeat(per_gpu // 8 + 1, 1, 1, 1)[:per_gpu].contiguous().pin_memory()
+    dev_x = host_x.to(dev)
+    tgt = torch.randint(0, 5, (per_gpu,), generator=torch.Generator().manual_seed(5 + rank)).to(dev)
+    torch.manual_seed(100 + rank)
+    host_loss = torch.zeros(1).pin_memory()
+
+    def one_step(x):
+        ddp.zero_grad()
+        loss = torch.nn.functional.cross_entropy(model(x).float(), tgt)
+        loss.backward()
+        ddp.finish()
+        opt.step()
+        return loss
+
+    def step():
+        return one_step(dev_x)
+
+    def step_e2e():
+        loss = one_step(host_x.to(dev, non_blocking=True))
+        host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss
+    return step, step_e2e, host_x.numel() * 4, 4
+
+
+def build_cls_oracle(size, batch, seed):
+    from cls_case import build_cls_model, oracle_cls_logits
+    from helpers import synth_images
+    _, sd = build_cls_model("global", 21, size=size)
+    leaf = {k: v.clone().requires_grad_(not k.endswith("pos_emb")) for k, v in sd.items()}
+    x = synth_images(batch, ["bscan"], seed=1234)["bscan"]
+    tgt = torch.arange(batch) % 5
+    depth_heads = (12, 12) if size == "base" else (24, 16)
+
+    def run():
+        from oracle import mirage_oracle as O
+        msd = {k[len("model."):]: v for k, v in leaf.items() if k.startswith("model.")}
+        tok = O.light_forward({"bscan": x}, msd, *depth_heads)
+        loss = torch.nn.functional.cross_entropy(O.cls_head(tok, leaf, "global"), tgt)
+        loss.backward()
+        for v in leaf.values():
+            v.grad = None
+        return loss
+    return run
+
+
 def build_pretrain_oracle(size, mods, batch, seed):
     from helpers import synth_images, synth_state_dict
     from pretrain_case import build_pretrain_model, oracle_step, sample_masks

@@ -454,9 +454,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const uint32_t k_tail_addr = smem_u32(smem + Cfg::kOffTail + (item_i & 1) * Cfg::kTailSlotBytes);
 #pragma unroll
           for (int t = 0; t < kMaxTail; ++t) {
-            if (t >= p.k_tail) break;
+            if (t >= p.k_tail) break;  // (unrolled over t only so that s_tail[] stays in registers)
             float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
+#pragma unroll 1  // once per item: keep it small, it is always instruction-cache cold
             for (int c = 0; c < 8; ++c) {
               const float4 qv = lds128(q_row_addr + ((static_cast<uint32_t>(c) ^ sw) << 4));
               const float4 kv4 = lds128(k_tail_addr + t * 128 + c * 16);
@@ -485,11 +485,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
         // whole S row -> registers, then hand the TMEM buffer straight back to the MMA warp
         uint32_t sreg[128];
+        float mxh[8];  // 8 independent max chains (the FMNMX latency, not its throughput, is what shows)
         if (warp_live) {
+          if (full_block) {
+            // two halves: the max over columns 0..63 runs under the TMEM load of columns 64..127
+            tmem_ld_32x32b_x32_p(t_s, sreg);
+            tmem_ld_32x32b_x32_p(t_s + 32, sreg + 32);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32_p(t_s + 64, sreg + 64);
+            tmem_ld_32x32b_x32_p(t_s + 96, sreg + 96);
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (c < nchunks) tmem_ld_32x32b_x32_p(t_s + c * 32, sreg + c * 32);
-          tmem_ld_wait();
+            for (int a = 0; a < 8; ++a) mxh[a] = fmaxf(__uint_as_float(sreg[a]), __uint_as_float(sreg[a + 8]));
+#pragma unroll
+            for (int i = 16; i < 64; i += 16) {
+#pragma unroll
+              for (int a = 0; a < 8; ++a)
+                mxh[a] = fmaxf(mxh[a], fmaxf(__uint_as_float(sreg[i + a]), __uint_as_float(sreg[i + a + 8])));
+            }
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < nchunks) tmem_ld_32x32b_x32_p(t_s + c * 32, sreg + c * 32);
+            tmem_ld_wait();
+          }
         }
         tc_fence_before();
         mbar_arrive(&s_free[g]);
@@ -499,17 +518,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (warp_live) {
           float mx0 = -INFINITY, mx1 = -INFINITY;
           if (full_block) {
-            float mx[8];  // 8 independent chains: the FMNMX latency, not its throughput, is what shows
 #pragma unroll
-            for (int a = 0; a < 8; ++a) mx[a] = fmaxf(__uint_as_float(sreg[a]), __uint_as_float(sreg[a + 8]));
-#pragma unroll
-            for (int i = 16; i < 128; i += 16) {
+            for (int i = 64; i < 128; i += 16) {
 #pragma unroll
               for (int a = 0; a < 8; ++a)
-                mx[a] = fmaxf(mx[a], fmaxf(__uint_as_float(sreg[i + a]), __uint_as_float(sreg[i + a + 8])));
+                mxh[a] = fmaxf(mxh[a], fmaxf(__uint_as_float(sreg[i + a]), __uint_as_float(sreg[i + a + 8])));
             }
-            mx0 = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-            mx1 = fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]));
+            mx0 = fmaxf(fmaxf(mxh[0], mxh[1]), fmaxf(mxh[2], mxh[3]));
+            mx1 = fmaxf(fmaxf(mxh[4], mxh[5]), fmaxf(mxh[6], mxh[7]));
           } else {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -588,8 +604,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    int ic[2] = {0, 0};
-    int pcnt[2] = {0, 0};
+    int ic0 = 0, ic1 = 0;      // items finished per group (scalars: the group loop is rolled)
+    int pcnt0 = 0, pcnt1 = 0;  // P V MMAs per group
     int item_i = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i) {
       const int pair = item % p.q_pairs;
@@ -599,20 +615,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (HD == 64 && p.k_tail > 0) mbar_wait(&q_full[item_i & 1], (item_i >> 1) & 1);
       const uint32_t v_tail_addr =
           smem_u32(smem + Cfg::kOffTail + (item_i & 1) * Cfg::kTailSlotBytes + kMaxTail * 128);
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (g >= n_groups) break;
+#pragma unroll 1
+      for (int g = 0; g < n_groups; ++g) {
         const int qrow = (pair * 2 + g) * 128 + r;
-        const float* st = stats + ((ic[g] & 1) * 2 + g) * (Cfg::kStatFields * 128);
-        mbar_wait(&stats_full[g], ic[g] & 1);
-        pcnt[g] += kvb;
-        mbar_wait(&o_full[g], (pcnt[g] - 1) & 1);  // the item's last P V retired
+        const int icg = g == 0 ? ic0 : ic1;
+        const int pcg = (g == 0 ? pcnt0 : pcnt1) + kvb;
+        if (g == 0) { pcnt0 = pcg; ++ic0; } else { pcnt1 = pcg; ++ic1; }
+        const float* st = stats + ((icg & 1) * 2 + g) * (Cfg::kStatFields * 128);
+        mbar_wait(&stats_full[g], icg & 1);
+        mbar_wait(&o_full[g], (pcg - 1) & 1);  // the item's last P V retired
         tc_fence_after();
         const float inv_l = st[0 * 128 + r];
         const bool row_ok = qrow < p.Nq_main;
         const uint32_t t_o = tmem_base + lane_off + 256 + g * 64;
         __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Nq + qrow) * p.ldo + h * HD;
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < HD / 16; ++c) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(t_o + c * 16, v);
@@ -655,7 +672,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_free[g]);
-        ++ic[g];
       }
       if (HD == 64 && p.k_tail > 0) {
         __syncwarp();
@@ -703,6 +719,9 @@ attn_tail_rows_kernel(const AttnDev p) {
     float mx = -INFINITY;
     for (int key = tid; key < p.Nk; key += kTailThreads) {
       const uint4* krow = reinterpret_cast<const uint4*>(kbase + static_cast<long long>(key) * p.ldk);
+      // the V row of this key is needed in phase 3: pull its 128-byte line towards L2 now, so the
+      // second phase of this CTA does not start with a full HBM round trip
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + static_cast<long long>(key) * p.ldv));
       float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
       for (int c = 0; c < HD / 8; ++c) {

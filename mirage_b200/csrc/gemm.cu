@@ -71,6 +71,12 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
   MB_REQUIRE(a->ldc % 8 == 0 || (a->epilogue & MB_EPI_UNPATCH),
              "mb_gemm: ldc=%lld must be a multiple of 8", (long long)a->ldc);
   MB_REQUIRE(a->a && a->b && a->out, "mb_gemm: null operand pointer");
+  MB_REQUIRE(((reinterpret_cast<uintptr_t>(a->a) | reinterpret_cast<uintptr_t>(a->b) |
+               reinterpret_cast<uintptr_t>(a->out) | reinterpret_cast<uintptr_t>(a->residual) |
+               reinterpret_cast<uintptr_t>(a->bias) | reinterpret_cast<uintptr_t>(a->aux_in) |
+               reinterpret_cast<uintptr_t>(a->aux_out)) & 15) == 0,
+             "mb_gemm: operand, output, bias, residual and aux pointers must be 16-byte aligned "
+             "(TMA boxes, 16-byte epilogue accesses, vector reductions)");
   MB_REQUIRE(a->k_splits >= 1, "mb_gemm: k_splits must be >= 1");
   MB_REQUIRE(a->k_splits == 1 || (a->epilogue & MB_EPI_ATOMIC),
              "mb_gemm: k_splits > 1 requires MB_EPI_ATOMIC");

@@ -47,30 +47,39 @@ class GradBucketAllReduce:
         # gradients become ready roughly in reverse registration order (output side first)
         params = params[::-1]
         cap = int(bucket_mb * 1024 * 1024 / 4)
+        # every gradient view starts on a 128-byte boundary inside its bucket: the kernels write them
+        # with 16-byte vector stores / vector reductions (a 5-element head bias must not shift the rest)
+        self._align = 32
+
+        def padded(n):
+            return (n + self._align - 1) // self._align * self._align
+
         groups: List[List[nn.Parameter]] = [[]]
         size = 0
         for p in params:
-            if size + p.numel() > cap and groups[-1]:
+            if size + padded(p.numel()) > cap and groups[-1]:
                 groups.append([])
                 size = 0
             groups[-1].append(p)
-            size += p.numel()
+            size += padded(p.numel())
         self.buckets: List[_Bucket] = []
         self._owner = {}
         self._reported = set()
+        self._offset = {}
         for g in groups:
-            n = sum(p.numel() for p in g)
+            n = sum(padded(p.numel()) for p in g)
             flat = torch.zeros(n, dtype=torch.float32, device=g[0].device)
             off = 0
             for p in g:
+                self._offset[p] = off
                 p.grad = flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
+                off += padded(p.numel())
             b = _Bucket(flat, g)
             self.buckets.append(b)
             for p in g:
                 self._owner[p] = b
                 p.register_post_accumulate_grad_hook(self._on_grad_ready)
-        self.num_params = sum(b.flat.numel() for b in self.buckets)
+        self.num_params = sum(p.numel() for b in self.buckets for p in b.params)
         # let the backward kernels accumulate straight into the bucket views (no temporary gradient,
         # no per-parameter add kernel); see mirage_b200.functional.set_grad_sink
         if direct and params[0].is_cuda:
@@ -114,11 +123,10 @@ class GradBucketAllReduce:
             b.flat.zero_()
             b.pending = len(b.params)
             b.work = None
-            off = 0
             for p in b.params:
+                off = self._offset[p]
                 if p.grad is None or p.grad.data_ptr() != b.flat.data_ptr() + 4 * off:
                     p.grad = b.flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
 
     def finish(self):
         """Block the current stream on every outstanding bucket; flush buckets whose hooks did not

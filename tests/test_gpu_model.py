@@ -153,3 +153,33 @@ def test_encode_host_pipeline_matches_forward():
         torch.cuda.synchronize()
         assert out.shape == ref.shape and out.is_pinned()
         assert_parity(out, ref, f"encode_host chunk={chunk}", max_rel=1e-5, cos=0.99999)
+
+
+@pytest.mark.parametrize("pool", ["global", "cls", "token_mix"])
+def test_cls_finetune_step_vs_reference_golden(pool):
+    """BASELINE configs[4] path at test size: miragecls_factory[pool] forward + CE + backward on cuda:0
+    against logits, loss and gradient norms recorded from the reference (tests/golden/cls.pt)."""
+    from cls_case import build_cls_model
+    dev = torch.device("cuda:0")
+    g = torch.load(GOLDEN / "cls.pt")
+    ref = g["out"][pool]
+    m, _ = build_cls_model(pool, g["weights_seed"], device=dev)
+    m.train()
+    x = synth_images(2, ["bscan"], seed=g["input_seed"])["bscan"].to(dev)
+    torch.manual_seed(g["mask_seed"])
+    logits = m(x)
+    assert logits.shape == ref["logits"].shape
+    scale = ref["logits"].abs().max().item()
+    assert (logits.detach().float().cpu() - ref["logits"]).abs().max().item() <= 2e-2 * scale
+    loss = torch.nn.functional.cross_entropy(logits.float(), torch.tensor([1, 3], device=dev))
+    assert abs(loss.item() - ref["loss"]) <= 2e-2 * abs(ref["loss"])
+    loss.backward()
+    hg = m.head.weight.grad.detach().float().cpu()
+    assert torch.nn.functional.cosine_similarity(hg.flatten(), ref["head_grad"].flatten(), dim=0).item() >= 0.999
+    big = max(ref["grad_norm"].values())
+    for k, n in ref["grad_norm"].items():
+        if n < 1e-4 * big:
+            continue
+        p = dict(m.named_parameters())[k]
+        assert p.grad is not None, k
+        assert abs(p.grad.norm().item() - n) <= 5e-2 * n, (k, p.grad.norm().item(), n)

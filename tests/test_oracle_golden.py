@@ -107,3 +107,22 @@ def test_pretrain_tiny_golden():
 
 def test_pretrain_base_golden():
     _pretrain_golden("base")
+
+
+def test_cls_heads_golden():
+    """Oracle of the classification tail (mirage_wrapper.py:187-244) against logits recorded from the
+    reference's miragecls_factory classes (ViT-B encoder, B=2)."""
+    import torch
+    from cls_case import build_cls_model, oracle_cls_logits
+    from helpers import GOLDEN, synth_images
+    g = torch.load(GOLDEN / "cls.pt")
+    x = synth_images(2, ["bscan"], seed=g["input_seed"])["bscan"]
+    for pool in ("global", "cls", "token_mix"):
+        m, sd = build_cls_model(pool, g["weights_seed"])
+        assert sum(p.numel() for p in m.parameters()) == g["out"][pool]["n_params"]
+        with torch.no_grad():
+            logits = oracle_cls_logits(x, sd, pool)
+        ref = g["out"][pool]["logits"]
+        assert torch.allclose(logits, ref, rtol=2e-3, atol=2e-3), (pool, (logits - ref).abs().max())
+        loss = torch.nn.functional.cross_entropy(logits, torch.tensor([1, 3])).item()
+        assert abs(loss - g["out"][pool]["loss"]) <= 2e-3 * abs(g["out"][pool]["loss"])
