@@ -155,6 +155,10 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
   int epi = EPI_GENERIC;
   const bool special = (a->epilogue & MB_EPI_UNPATCH) || a->out_row_period > 0 ||
                        (a->residual && a->res_period > 0);
+  if (special && p.out_f32 && !(a->epilogue & (MB_EPI_GELU | MB_EPI_DGELU | MB_EPI_ATOMIC)) &&
+      !((a->epilogue & MB_EPI_UNPATCH) && a->up_pw % 4 != 0)) {
+    epi = EPI_MAP;  // bias (+ residual / pos-emb rows) -> fp32 through a row map or the un-patchify map
+  }
   if (!special) {
     if (a->epilogue & MB_EPI_GELU) {
       if (!p.out_f32 && !a->residual && !(a->epilogue & (MB_EPI_DGELU | MB_EPI_ATOMIC))) epi = EPI_GELU;

@@ -59,8 +59,11 @@ enum : int {
   EPI_RES = 2,      // (+bias) + fp32 residual[row] -> fp32              proj / fc2 (in place allowed)
   EPI_DGELU = 3,    // * GELU'(aux_in) -> bf16                           dgrad through the GELU
   EPI_F32 = 4,      // (+bias) -> fp32, plain store or atomic add        wgrad (split-K), fp32 outputs
-  EPI_GENERIC = 5,  // everything at run time: row maps, periodic residual, un-patchify, ...
-  EPI_COUNT = 6
+  EPI_GENERIC = 5,  // everything at run time (any combination; slow: integer divisions per chunk)
+  EPI_MAP = 6,      // (+bias) (+fp32 residual, optionally periodic = pos-emb rows) -> fp32 through an
+                    // output map (row map or un-patchify), index math hoisted out of the element loops:
+                    // patch / semseg embedding into the token buffer, out_proj into image layout
+  EPI_COUNT = 7
 };
 
 constexpr int kGemmThreads = 384;
@@ -203,7 +206,33 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
   const uint32_t wr_sw = static_cast<uint32_t>(lane & 7);
 
   EpiRegs<MODE> cur, nxt;
-  if constexpr (MODE != EPI_GENERIC) epi_prefetch<MODE>(p, cur, row_base, n_base + j4 * 4, first_split, sub);
+  if constexpr (MODE != EPI_GENERIC && MODE != EPI_MAP)
+    epi_prefetch<MODE>(p, cur, row_base, n_base + j4 * 4, first_split, sub);
+  // EPI_MAP: row part of the output index and residual row of this thread's 8 rows, once per tile
+  [[maybe_unused]] long long map_out[MODE == EPI_MAP ? 8 : 1];
+  [[maybe_unused]] long long map_res[MODE == EPI_MAP ? 8 : 1];
+  [[maybe_unused]] const bool unpatch = (p.epilogue & MB_EPI_UNPATCH) != 0;
+  if constexpr (MODE == EPI_MAP) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row_base + it * 4 + sub;
+      map_res[it] = p.res_period > 0 ? row % p.res_period : row;
+      if (unpatch) {
+        const int per_img = p.up_gh * p.up_gw;
+        const int bi = row / per_img, t = row - bi * per_img;
+        const int nh = t / p.up_gw, nw = t - nh * p.up_gw;
+        map_out[it] = ((static_cast<long long>(bi) * p.up_c) * (p.up_gh * p.up_ph) + static_cast<long long>(nh) * p.up_ph) *
+                          (static_cast<long long>(p.up_gw) * p.up_pw) +
+                      static_cast<long long>(nw) * p.up_pw;
+      } else {
+        const long long orow =
+            p.orow_period > 0
+                ? static_cast<long long>(row / p.orow_period) * p.orow_stride + row % p.orow_period + p.orow_offset
+                : static_cast<long long>(row);
+        map_out[it] = orow * p.ldc;
+      }
+    }
+  }
 
   mbar_wait(full_bar, full_parity);  // accumulator of this tile is complete
   tc_fence_after();
@@ -212,7 +241,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
   for (int c = 0; c < NSLABS; ++c) {
     const int col0 = n_base + c * 32;
     if (col0 >= p.N) break;  // warp-uniform
-    if constexpr (MODE != EPI_GENERIC) {
+    if constexpr (MODE != EPI_GENERIC && MODE != EPI_MAP) {
       if (c + 1 < NSLABS) epi_prefetch<MODE>(p, nxt, row_base, col0 + 32 + j4 * 4, first_split, sub);
     }
     // ---- phase A
@@ -241,6 +270,31 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
       for (int it = 0; it < 8; ++it) {
         const int row = row_base + it * 4 + sub;
         if (row < p.M && col_ok) epi_generic_chunk(p, acc[it], row, col, first_split);
+      }
+    } else if constexpr (MODE == EPI_MAP) {
+      // per-slab column part of the output index (un-patchify: col -> (channel, py, px))
+      long long ocol = col;
+      if (unpatch) {
+        const int pp = p.up_ph * p.up_pw;
+        const int ch = col / pp, rr2 = col - ch * pp;
+        const int py = rr2 / p.up_pw, px = rr2 - py * p.up_pw;
+        ocol = (static_cast<long long>(ch) * (p.up_gh * p.up_ph) + py) * (static_cast<long long>(p.up_gw) * p.up_pw) + px;
+      }
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = row_base + it * 4 + sub;
+        if (row < p.M && col_ok) {
+          float f0 = acc[it].x + bias4.x, f1 = acc[it].y + bias4.y, f2 = acc[it].z + bias4.z,
+                f3 = acc[it].w + bias4.w;
+          if (p.residual != nullptr) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + map_res[it] * p.ld_res + col));
+            f0 += r.x; f1 += r.y; f2 += r.z; f3 += r.w;
+          }
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + map_out[it] + ocol) =
+              make_float4(f0, f1, f2, f3);
+        }
       }
     } else {
       const long long row0 = row_base + sub;

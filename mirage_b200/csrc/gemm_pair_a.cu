@@ -25,6 +25,10 @@ int dispatch_gemm_pair_a(int bn, int layout, int epi, const CUtensorMap& ta, con
     return launch_gemm_pair<128, MB_MAJOR_K, 0, 2, 4>(ta, tb, p, stream);
   if (layout == LAY_KK_BF16 && bn == 128 && epi == 5)
     return launch_gemm_pair<128, MB_MAJOR_K, 0, 2, 5>(ta, tb, p, stream);
+  if (layout == LAY_KK_BF16 && bn == 256 && epi == 6)
+    return launch_gemm_pair<256, MB_MAJOR_K, 0, 2, 6>(ta, tb, p, stream);
+  if (layout == LAY_KK_BF16 && bn == 128 && epi == 6)
+    return launch_gemm_pair<128, MB_MAJOR_K, 0, 2, 6>(ta, tb, p, stream);
   return 1;  // no specialised instantiation
 }
 

@@ -25,6 +25,10 @@ int dispatch_gemm_single_a(int bn, int layout, int epi, const CUtensorMap& ta, c
     return launch_gemm_single<64, MB_MAJOR_K, 0, 2, 4>(ta, tb, p, stream);
   if (layout == LAY_KK_BF16 && bn == 64 && epi == 5)
     return launch_gemm_single<64, MB_MAJOR_K, 0, 2, 5>(ta, tb, p, stream);
+  if (layout == LAY_KK_BF16 && bn == 128 && epi == 6)
+    return launch_gemm_single<128, MB_MAJOR_K, 0, 2, 6>(ta, tb, p, stream);
+  if (layout == LAY_KK_BF16 && bn == 64 && epi == 6)
+    return launch_gemm_single<64, MB_MAJOR_K, 0, 2, 6>(ta, tb, p, stream);
   return 1;  // no specialised instantiation
 }
 

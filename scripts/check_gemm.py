@@ -245,6 +245,32 @@ def _time(fn, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
+def group_maps():
+    """EPI_MAP: output row map, periodic residual, un-patchify -- specialised epilogue vs torch."""
+    ok = True
+    # un-patchify: tokens [B*gh*gw, C*ph*pw] -> image [B, C, gh*ph, gw*pw]
+    for (B, C_, ph, pw, gh, gw, k) in [(3, 1, 32, 32, 16, 16, 256), (2, 13, 8, 8, 16, 16, 256), (1, 1, 32, 32, 16, 16, 64)]:
+        m, n = B * gh * gw, C_ * ph * pw
+        a, w = mk(m, k), mk(n, k, scale=k ** -0.5)
+        bias = torch.randn(n, device=dev)
+        img = ops.gemm(a, w, m=m, n=n, k=k, bias=bias, out_dtype=torch.float32, unpatch=(C_, ph, pw, gh, gw))
+        ref = (a.float() @ w.float().t() + bias).reshape(B, gh, gw, C_, ph, pw).permute(0, 3, 1, 4, 2, 5)
+        ok &= report(f"unpatch B={B} C={C_} p={ph}", img.reshape(B * C_ * gh * ph, gw * pw),
+                     ref.reshape(B * C_ * gh * ph, gw * pw), tol=5e-3)
+    # row map + periodic residual: tokens of one modality written into a [B, 513, D] buffer at offset 256
+    B, ntok, d, k = 5, 256, 512, 256
+    a, w = mk(B * ntok, k), mk(d, k, scale=k ** -0.5)
+    bias, pos = torch.randn(d, device=dev), torch.randn(ntok, d, device=dev)
+    buf = torch.full((B, 513, d), 7.0, device=dev)
+    ops.gemm(a, w, m=B * ntok, n=d, k=k, bias=bias, residual=pos, res_period=ntok, out=buf.view(B * 513, d),
+             out_row_map=(ntok, 513, 256))
+    ref = (a.float() @ w.float().t() + bias).view(B, ntok, d) + pos
+    ok &= report("row map + periodic residual", buf[:, 256:512].reshape(-1, d), ref.reshape(-1, d), tol=5e-3)
+    untouched = bool((buf[:, :256] == 7.0).all() and (buf[:, 512:] == 7.0).all())
+    print(f"[{'PASS' if untouched else 'FAIL'}] row map leaves the other rows untouched", flush=True)
+    return ok and untouched
+
+
 def group_perfepi():
     """Epilogue variants of the encoder's GEMMs at cfg-2 size (the tile loop is identical; only the
     epilogue differs), against the plain bf16 store."""
@@ -265,6 +291,19 @@ def group_perfepi():
             fn = lambda: ops.gemm(a, w, m=m, n=n, k=k, bias=bias, out=out)
         ms = _time(fn)
         print(f"[PERF] {what:9s} m={m} n={n} k={k}: {ms:.3f} ms = {2.0 * m * n * k / ms / 1e9:.0f} TFLOP/s", flush=True)
+    # patch embedding (tf32, image read by TMA boxes) and out_proj + un-patchify at cfg-4 size
+    img = torch.rand(256, 1, 512, 512, device=dev)
+    w = torch.randn(1024, 1024, device=dev) * 0.03
+    bias, pos = torch.randn(1024, device=dev), torch.randn(256, 1024, device=dev)
+    out = torch.empty(256 * 256, 1024, device=dev)
+    ms = _time(lambda: ops.gemm(img, w, m=65536, n=1024, k=1024, a_layout=L.MB_A_PATCH32, img_hw=(512, 512),
+                                bias=bias, residual=pos, res_period=256, out=out))
+    print(f"[PERF] patch-embed tf32 65536x1024x1024 +bias+pos: {ms:.3f} ms = {2.0 * 65536 * 1024 * 1024 / ms / 1e9:.0f} TFLOP/s",
+          flush=True)
+    a, w2 = mk(65536, 256), mk(1024, 256, scale=1 / 16)
+    ms = _time(lambda: ops.gemm(a, w2, m=65536, n=1024, k=256, bias=bias, out_dtype=torch.float32,
+                                unpatch=(1, 32, 32, 16, 16)))
+    print(f"[PERF] out_proj+unpatch 65536x1024x256: {ms:.3f} ms = {65536 * 1024 * 4 / ms / 1e6:.0f} GB/s written", flush=True)
     return True
 
 

@@ -19,7 +19,7 @@ def _load(name):
     return mod
 
 
-@pytest.mark.parametrize("group", ["basic", "epilogue", "dgrad", "wgrad", "patch", "pair"])
+@pytest.mark.parametrize("group", ["basic", "epilogue", "dgrad", "wgrad", "patch", "pair", "maps"])
 def test_gemm(group):
     assert getattr(_load("check_gemm"), f"group_{group}")()
 
