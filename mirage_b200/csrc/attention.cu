@@ -15,12 +15,16 @@
 //   warp 1       TMEM allocator + MMA issuer (one lane), S always one block ahead of P V:
 //                    S_g = Q_g K_j^T      (SS: both operands K-major in smem, accumulator S_g in TMEM)
 //                    O_g += P_g V_j       (TS: P_g read from TMEM as the A operand, V MN-major in smem)
-//   warps 4-7    softmax group 0, one thread per query row, no shuffles (208 registers)
-//   warps 8-11   softmax group 1
-//   warps 12-15  epilogue: O_g / l -> bf16 -> global (+ LSE) once the item's last P V retired, so the
+//   warps 4-11   softmax group 0: TWO threads per query row (warps 4-7 own key columns [0,64) of the
+//   warps 12-19  softmax group 1   block, warps 8-11 columns [64,128)); the two halves exchange their
+//                row maxima through smem + a named barrier, everything else is thread-private.  Four
+//                softmax warps per SM sub-partition instead of two: the first layout (one thread per
+//                row, 128 values in registers) left the MUFU idle 2/3 of the time for lack of warps to
+//                switch to (ncu r01 v5: issue 38 %, XU 36 %, top stall "wait")
+//   warps 20-23  epilogue: O_g / l -> bf16 -> global (+ LSE) once the item's last P V retired, so the
 //                softmax warps never wait for the drain of their own accumulator
 //
-// Each softmax thread pulls its whole S row (128 fp32) into registers with one round of tcgen05.ld and
+// Each softmax thread pulls its half S row (64 fp32) into registers with one round of tcgen05.ld and
 // releases the S buffer at once (s_free): S_g(j+1) runs while the row is being exponentiated.  The
 // exponentials are packed to bf16 in registers and written back to TMEM (P_g) with tcgen05.st -- no
 // shared-memory round trip, no proxy fence.  Softmax runs in the log2 domain with a running max m and
@@ -58,7 +62,7 @@ struct AttnDev {
 
 constexpr int kMaxTail = 4;  // largest remainder (mod 128) that is peeled off instead of padded
 
-constexpr int kAttnThreads = 512;  // 4 warpgroups: {TMA, MMA, -, -}, softmax 0, softmax 1, epilogue
+constexpr int kAttnThreads = 768;  // 6 warpgroups: {TMA, MMA, MMA, -}, 4 x softmax (group, column half), epilogue
 constexpr int kKvStages = 3;
 constexpr int kDefaultPoly = 0;
 constexpr int kDefaultStagger = 0;
@@ -74,9 +78,10 @@ struct AttnCfg {
   static constexpr int kOffTail = kOffV + kKvStages * kTileBytes;  // 2 slots x {k rows, v rows}
   static constexpr int kTailSlotBytes = 2 * kMaxTail * 128;
   static constexpr int kOffStats = kOffTail + 2 * kTailSlotBytes;  // [parity][group][field][row] f32
-  static constexpr int kStatFields = 2 + kMaxTail;                 // 1/l, lse, e_tail[]
+  static constexpr int kStatFields = 3 + kMaxTail;                 // l (half 0), l (half 1), m, e_tail[]
   static constexpr int kStatsBytes = 2 * 2 * kStatFields * 128 * 4;
-  static constexpr int kOffBar = kOffStats + kStatsBytes;
+  static constexpr int kOffXchg = kOffStats + kStatsBytes;         // [parity][group][half][row] f32 row maxima
+  static constexpr int kOffBar = kOffXchg + 2 * 2 * 2 * 128 * 4;
   static constexpr int kSmemBytes = kOffBar + 512;
   static constexpr int kSwizzle = (HD == 64) ? 128 : 64;
 };
@@ -155,8 +160,8 @@ __device__ __forceinline__ void fadd2_v(float& s0, float& s1, uint32_t a0, uint3
       : "r"(a0), "r"(a1));
 }
 
-// exponentiate one S row held in registers: sreg[i] (fp32 bits, i < 32*nchunks) -> packed bf16 pairs
-// in sreg[i/2]; returns the row sum.  FULL: all 128 columns valid, no masking code at all.
+// exponentiate one half S row (64 columns) held in registers: sreg[i] (fp32 bits, i < 32*nchunks) ->
+// packed bf16 pairs in sreg[i/2]; returns the row sum.  FULL: all 64 columns valid, no masking code.
 // Three passes in pinned program order, each a run of mutually independent instructions (the
 // compiler's own interleaving left every instruction waiting on its predecessor: ncu r01 v4, 7 clk per
 // instruction with 'wait' the top stall):  x = s*scale - m (64 FFMA2);  e = 2^x in place (128 MUFU,
@@ -164,17 +169,17 @@ __device__ __forceinline__ void fadd2_v(float& s0, float& s1, uint32_t a0, uint3
 // the SM sub-partition issues into the gaps);  row sum on 4 independent FADD2 chains + bf16 packing.
 // POLY: of every 16 element pairs, this many go through exp2_poly2 instead of MUFU.EX2.
 template <bool FULL, int POLY>
-__device__ __forceinline__ float exp_row(uint32_t (&sreg)[128], float scale_log2, float neg_m, int valid,
+__device__ __forceinline__ float exp_row(uint32_t (&sreg)[64], float scale_log2, float neg_m, int valid,
                                          int nchunks) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     if (FULL || c < nchunks) {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) ffma2_v(sreg[c * 32 + i], sreg[c * 32 + i + 1], scale_log2, neg_m);
     }
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     if (FULL || c < nchunks) {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
@@ -199,7 +204,7 @@ __device__ __forceinline__ float exp_row(uint32_t (&sreg)[128], float scale_log2
 #pragma unroll
   for (int a = 0; a < 8; ++a) sum[a] = 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     if (FULL || c < nchunks) {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
@@ -230,14 +235,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* v_full = bars + 10;               // 3
   uint64_t* v_empty = bars + 13;              // 3
   uint64_t* s_full = bars + 16;               // 2   MMA commit: S_g(j) complete
-  uint64_t* s_free = bars + 18;               // 2   128 softmax threads: S_g copied to registers
-  uint64_t* p_full = bars + 20;               // 2   128 softmax threads: P_g(j) in TMEM
+  uint64_t* s_free = bars + 18;               // 2   256 softmax threads: S_g copied to registers
+  uint64_t* p_full = bars + 20;               // 2   256 softmax threads: P_g(j) in TMEM
   uint64_t* o_full = bars + 22;               // 2   MMA commit: P_g V(j) retired
   uint64_t* o_free = bars + 24;               // 2   4 epilogue warps: O_g of the item read out
-  uint64_t* stats_full = bars + 26;           // 2   128 softmax threads: row statistics of the item
+  uint64_t* stats_full = bars + 26;           // 2   256 softmax threads: row statistics of the item
   uint64_t* tail_free = bars + 28;            // 2   4 epilogue warps: tail rows of the item slot consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
   float* stats = reinterpret_cast<float*>(smem + Cfg::kOffStats);
+  float* xchg = reinterpret_cast<float*>(smem + Cfg::kOffXchg);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -267,11 +273,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&s_free[g], 128);
-      mbar_init(&p_full[g], 128);
+      mbar_init(&s_free[g], 256);
+      mbar_init(&p_full[g], 256);
       mbar_init(&o_full[g], 1);
       mbar_init(&o_free[g], 4);
-      mbar_init(&stats_full[g], 128);
+      mbar_init(&stats_full[g], 256);
     }
     mbar_fence_init();
   }
@@ -410,25 +416,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
-  } else if (warp < 12) {
+  } else if (warp < 20) {
     // ---------------------------------------------------------------- softmax
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-    const int g = (warp - 4) >> 2;
+    // register pool of the CTA = 768 threads x 80 at launch = 61440 = 128 x (48 + 4 x 96 + 48)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    const int sgi = (warp - 4) >> 2;
+    const int g = sgi >> 1;        // query tile of the item
+    const int hf = sgi & 1;        // key columns [hf*64, hf*64+64) of every block
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                    // row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_off + g * 128;
+    const uint32_t t_s = tmem_base + lane_off + g * 128 + hf * 64;
     const uint32_t t_o = tmem_base + lane_off + 256 + g * 64;
-    const uint32_t t_p = tmem_base + lane_off + 384 + g * 64;
+    const uint32_t t_p = tmem_base + lane_off + 384 + g * 64 + hf * 32;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    // The two groups are symmetric, so whatever phase offset they start with persists.  Started
-    // together they exponentiate at the same time and fight for the MUFU, then both leave it idle;
-    // delaying group 1 once by about half a key block interleaves them.
-    if (g == 1 && p.stagger > 0) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < p.stagger) {
-      }
-    }
     int cnt = 0;   // key blocks this group has processed (phases of s_full / o_full)
     int ic = 0;    // items this group has processed     (stats slot / phases of stats_full, o_free)
     int item_i = 0;
@@ -438,16 +439,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (pair * 2 + g >= p.q_tiles) continue;            // this group has no tile in the item
       const bool warp_live = (pair * 2 + g) * 128 + quarter * 32 < p.Nq_main;
       float m_run = -INFINITY;
-      float l_run = 0.f;
+      float l_run = 0.f;  // sum over THIS half's columns; the halves are added by the epilogue
 
       // Peeled key tail (HD == 64, host-guaranteed kv_blocks >= 2 so the Q slot outlives this read):
       // s_tail[t] = <q_row, k_tail_t> on CUDA cores, q from the swizzled smem tile, k_tail broadcast
-      // from the item's tail slot.  The scores join the LAST key block's max / sum.
+      // from the item's tail slot.  Column half 0 owns the tail: its scores join that half's max and
+      // sum of the LAST key block.
       float s_tail[kMaxTail];
 #pragma unroll
       for (int t = 0; t < kMaxTail; ++t) s_tail[t] = -INFINITY;
       if constexpr (HD == 64) {
-        if (p.k_tail > 0) {
+        if (p.k_tail > 0 && hf == 0) {
           mbar_wait(&q_full[item_i & 1], (item_i >> 1) & 1);
           const uint32_t q_row_addr =
               smem_u32(smem + Cfg::kOffQ + ((item_i & 1) * 2 + g) * Cfg::kTileBytes + r * 128);
@@ -478,22 +480,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int t = 0; t < kMaxTail; ++t) e_tail[t] = 0.f;
 
       for (int j = 0; j < kvb; ++j, ++cnt) {
-        const int valid = min(128, p.Nk_main - j * 128);
+        const int valid_blk = min(128, p.Nk_main - j * 128);
+        const int valid = max(0, min(64, valid_blk - hf * 64));  // valid columns of this half
         const int nchunks = (valid + 31) >> 5;
-        const bool full_block = (valid == 128);
+        const bool full_block = (valid == 64);
         mbar_wait(&s_full[g], cnt & 1);
         tc_fence_after();
-        // whole S row -> registers, then hand the TMEM buffer straight back to the MMA warp
-        uint32_t sreg[128];
-        float mxh[8];  // 8 independent max chains (the FMNMX latency, not its throughput, is what shows)
+        // half S row -> registers, then hand the TMEM buffer straight back to the MMA warp
+        uint32_t sreg[64];
+        if (warp_live) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (c < nchunks) tmem_ld_32x32b_x32_p(t_s + c * 32, sreg + c * 32);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(&s_free[g]);
+
+        // local max over this half's columns (8 independent chains), then the row max across halves
+        float mx_loc = -INFINITY;
         if (warp_live) {
           if (full_block) {
-            // two halves: the max over columns 0..63 runs under the TMEM load of columns 64..127
-            tmem_ld_32x32b_x32_p(t_s, sreg);
-            tmem_ld_32x32b_x32_p(t_s + 32, sreg + 32);
-            tmem_ld_wait();
-            tmem_ld_32x32b_x32_p(t_s + 64, sreg + 64);
-            tmem_ld_32x32b_x32_p(t_s + 96, sreg + 96);
+            float mxh[8];
 #pragma unroll
             for (int a = 0; a < 8; ++a) mxh[a] = fmaxf(__uint_as_float(sreg[a]), __uint_as_float(sreg[a + 8]));
 #pragma unroll
@@ -502,45 +510,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               for (int a = 0; a < 8; ++a)
                 mxh[a] = fmaxf(mxh[a], fmaxf(__uint_as_float(sreg[i + a]), __uint_as_float(sreg[i + a + 8])));
             }
-            tmem_ld_wait();
+            mx_loc = fmaxf(fmaxf(fmaxf(mxh[0], mxh[1]), fmaxf(mxh[2], mxh[3])),
+                           fmaxf(fmaxf(mxh[4], mxh[5]), fmaxf(mxh[6], mxh[7])));
           } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (c < nchunks) tmem_ld_32x32b_x32_p(t_s + c * 32, sreg + c * 32);
-            tmem_ld_wait();
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(&s_free[g]);
-
-        float alpha = 1.f;
-        bool rescale = false;
-        if (warp_live) {
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-          if (full_block) {
-#pragma unroll
-            for (int i = 64; i < 128; i += 16) {
-#pragma unroll
-              for (int a = 0; a < 8; ++a)
-                mxh[a] = fmaxf(mxh[a], fmaxf(__uint_as_float(sreg[i + a]), __uint_as_float(sreg[i + a + 8])));
-            }
-            mx0 = fmaxf(fmaxf(mxh[0], mxh[1]), fmaxf(mxh[2], mxh[3]));
-            mx1 = fmaxf(fmaxf(mxh[4], mxh[5]), fmaxf(mxh[6], mxh[7]));
-          } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
               if (c < nchunks) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                  if (c * 32 + i < valid) mx0 = fmaxf(mx0, __uint_as_float(sreg[c * 32 + i]));
+                  if (c * 32 + i < valid) mx_loc = fmaxf(mx_loc, __uint_as_float(sreg[c * 32 + i]));
               }
             }
           }
           if (HD == 64 && j == kvb - 1) {
 #pragma unroll
-            for (int t = 0; t < kMaxTail; ++t) mx0 = fmaxf(mx0, s_tail[t]);  // -inf when unused
+            for (int t = 0; t < kMaxTail; ++t) mx_loc = fmaxf(mx_loc, s_tail[t]);  // -inf when unused / half 1
           }
-          const float m_cand = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
+        }
+        // exchange (double-buffered by block parity; one named barrier per block and group)
+        float* xc = xchg + ((cnt & 1) * 4 + g * 2) * 128;
+        xc[hf * 128 + r] = mx_loc;
+        named_bar_sync(1 + g, 256);
+        const float mx_row = fmaxf(mx_loc, xc[(hf ^ 1) * 128 + r]);
+
+        float alpha = 1.f;
+        bool rescale = false;
+        if (warp_live) {
+          // identical in both halves: same row maxima, same warp quarter -> same lazy decision
+          const float m_cand = fmaxf(m_run, mx_row * p.scale_log2);
           if (j == 0) {
             m_run = m_cand;  // nothing accumulated yet: P V(0) overwrites O
           } else if (__any_sync(0xffffffffu, m_cand > m_run + kLazyMaxLog2)) {
@@ -550,8 +547,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             rescale = true;
           }
           const float neg_m = -m_run;
-          float sum = full_block ? exp_row<true, POLY>(sreg, p.scale_log2, neg_m, valid, nchunks)
-                                 : exp_row<false, POLY>(sreg, p.scale_log2, neg_m, valid, nchunks);
+          float sum = 0.f;
+          if (full_block) sum = exp_row<true, POLY>(sreg, p.scale_log2, neg_m, valid, nchunks);
+          else if (nchunks > 0) sum = exp_row<false, POLY>(sreg, p.scale_log2, neg_m, valid, nchunks);
           if (HD == 64 && j == kvb - 1) {
 #pragma unroll
             for (int t = 0; t < kMaxTail; ++t) {
@@ -565,20 +563,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(&o_full[g], (cnt - 1) & 1);  // previous P V of this group retired: P_g free, O_g stable
           tc_fence_after();
         }
-        if (rescale) {  // warp-uniform, rare
-#pragma unroll
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_o + c * 32, v);
+        if (rescale && hf == 0) {  // warp-uniform, rare; column half 0 rescales the shared accumulator
+#pragma unroll 1
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_o + c * 16, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_32x32b_x32(t_o + c * 32, v);
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x16(t_o + c * 16, v);
           }
         }
         if (warp_live) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c)
             if (c < nchunks) tmem_st_32x32b_x16_p(t_p + c * 16, sreg + c * 16);
         }
         tmem_st_wait();
@@ -590,10 +588,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (ic > 0) mbar_wait(&o_free[g], (ic - 1) & 1);  // keeps stats_full at most one phase ahead
       {
         float* st = stats + ((ic & 1) * 2 + g) * (Cfg::kStatFields * 128);
-        st[0 * 128 + r] = 1.f / l_run;
-        st[1 * 128 + r] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+        st[hf * 128 + r] = l_run;
+        if (hf == 0) {
+          st[2 * 128 + r] = m_run;
 #pragma unroll
-        for (int t = 0; t < kMaxTail; ++t) st[(2 + t) * 128 + r] = e_tail[t];
+          for (int t = 0; t < kMaxTail; ++t) st[(3 + t) * 128 + r] = e_tail[t];
+        }
       }
       mbar_arrive(&stats_full[g]);
       ++ic;
@@ -625,7 +625,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&stats_full[g], icg & 1);
         mbar_wait(&o_full[g], (pcg - 1) & 1);  // the item's last P V retired
         tc_fence_after();
-        const float inv_l = st[0 * 128 + r];
+        const float l_row = st[0 * 128 + r] + st[1 * 128 + r];  // the two column halves
+        const float inv_l = 1.f / l_row;
         const bool row_ok = qrow < p.Nq_main;
         const uint32_t t_o = tmem_base + lane_off + 256 + g * 64;
         __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Nq + qrow) * p.ldo + h * HD;
@@ -638,7 +639,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
             for (int t = 0; t < kMaxTail; ++t) {  // O += p_tail * v_tail (peeled keys)
               if (t >= p.k_tail) break;
-              const float e = st[(2 + t) * 128 + r];
+              const float e = st[(3 + t) * 128 + r];
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
                 const float4 vv = lds128(v_tail_addr + t * 128 + c * 32 + u * 16);
@@ -668,7 +669,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
         if (p.lse != nullptr && row_ok)
-          p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qrow] = st[1 * 128 + r];
+          p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qrow] =
+              (st[2 * 128 + r] + log2f(l_row)) * 0.6931471805599453f;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_free[g]);
@@ -719,9 +721,6 @@ attn_tail_rows_kernel(const AttnDev p) {
     float mx = -INFINITY;
     for (int key = tid; key < p.Nk; key += kTailThreads) {
       const uint4* krow = reinterpret_cast<const uint4*>(kbase + static_cast<long long>(key) * p.ldk);
-      // the V row of this key is needed in phase 3: pull its 128-byte line towards L2 now, so the
-      // second phase of this CTA does not start with a full HBM round trip
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + static_cast<long long>(key) * p.ldv));
       float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
       for (int c = 0; c < HD / 8; ++c) {
