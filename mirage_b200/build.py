@@ -25,6 +25,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_flags() -> list[str]:
+    """Extra nvcc flags from the environment, e.g. MB_NVCC_EXTRA=-DMB_DEBUG_BARRIERS (debug builds)."""
+    return os.environ.get("MB_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and Path(cand).exists():
@@ -56,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         obj = OBJ_DIR / (src.stem + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+            cmd = [nvcc, *NVCC_FLAGS, *_extra_flags(), "-c", str(src), "-o", str(obj)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)

@@ -53,7 +53,10 @@ struct AttnDev {
   // extra 128-row work item and an extra key block, so it is peeled off instead:
   //   k_tail keys   -> rank-1 update on CUDA cores (scores in the softmax threads, P_tail V_tail in
   //                    the epilogue warps); the rows travel to smem with the item's Q tiles
-  //   q_tail rows   -> attn_tail_rows_kernel (CUDA cores, one CTA per (batch, head))
+  //   q_tail rows   -> attn_tail_rows_kernel (CUDA cores, one CTA per (batch, head)).  Computing that row
+//                    inside this kernel (epilogue warps reading the K / V stages from smem) was tried
+//                    and was slower: the extra release count on every K / V stage couples the ring to
+//                    the slowest warps (0.79-0.85 ms vs 0.69 ms at cfg 2)
   int Nq_main, Nk_main, k_tail;
   int q_tiles, q_pairs, kv_blocks;
   int stagger;  // cycles softmax group 1 idles once at kernel start (anti-phases the two groups)

@@ -69,6 +69,11 @@ def group_attn64():
     ok &= attn_case(2, 2, 513, 256, 64, self_attn=False)   # query tail only
     ok &= attn_case(2, 2, 129, 129, 64)                    # query tail peeled, keys padded (nk < 256)
     ok &= attn_case(2, 2, 133, 261, 64, self_attn=False)   # remainder 5: nothing peeled
+    # many work items per persistent CTA (cross-item pipeline, ring release by the epilogue warps)
+    ok &= attn_case(24, 16, 513, 513, 64)
+    ok &= attn_case(40, 16, 257, 257, 64)
+    ok &= attn_case(64, 16, 99, 99, 64)
+    ok &= attn_case(20, 16, 514, 514, 64)                  # two peeled rows: separate tail kernel
     return ok
 
 
