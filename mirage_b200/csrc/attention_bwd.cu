@@ -12,7 +12,7 @@
 // The (j, i) iterations of ALL items form one software pipeline (the first version ran one CTA per
 // item with every stage serialised: 228 us for the 4096 (b, h) problems of cfg 4, 15k clk per item):
 //
-//   warp 0       TMA producer: K_j, V_j per key block (2 slots); Q_i, dO_i per iteration (2 slots)
+//   warp 0       TMA producer: K_j, V_j per key block (2 slots); Q_i, dO_i, O_i per iteration (2 slots)
 //   warp 1       MMA issuer (one lane):  MMA1(t+1) = {S, dP}  is issued as soon as the compute warps have
 //                copied S/dP(t) to registers, i.e. it overlaps the exponentials of iteration t and MMA2(t)
 //   warps 4-7    compute, key columns [0, 64)   of the tile: one thread per query row holds 64 S + 64 dP
@@ -54,7 +54,8 @@ struct AttnBwdCfg {
   static constexpr int kOffV = kOffK + 2 * kTileBytes;
   static constexpr int kOffQ = kOffV + 2 * kTileBytes;
   static constexpr int kOffDO = kOffQ + 2 * kTileBytes;
-  static constexpr int kOffP = kOffDO + 2 * kTileBytes;
+  static constexpr int kOffO = kOffDO + 2 * kTileBytes;   // forward output tile: D = rowsum(dO o O) from smem
+  static constexpr int kOffP = kOffO + 2 * kTileBytes;
   static constexpr int kOffDS = kOffP + kPBytes;
   static constexpr int kOffBar = kOffDS + kPBytes;
   static constexpr int kSmemBytes = kOffBar + 256;
@@ -65,7 +66,7 @@ template <int HD>
 __global__ void __launch_bounds__(kAttnBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                const AttnBwdDev p) {
+                const __grid_constant__ CUtensorMap tm_o, const AttnBwdDev p) {
   using Cfg = AttnBwdCfg<HD>;
   constexpr uint64_t kSw = (HD == 64) ? kDescSwizzle128B : kDescSwizzle64B;
   constexpr uint32_t kSbo = 8 * Cfg::kRowBytes;
@@ -96,6 +97,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_o);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
@@ -136,9 +138,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           for (int i = 0; i < qt; ++i, ++t) {
             const int qs = t & 1;
             mbar_wait(&qdo_empty[qs], ((t >> 1) & 1) ^ 1);
-            mbar_arrive_expect_tx(&qdo_full[qs], 2 * Cfg::kTileBytes);
+            mbar_arrive_expect_tx(&qdo_full[qs], 3 * Cfg::kTileBytes);
             tma_load_3d(smem + Cfg::kOffQ + qs * Cfg::kTileBytes, &tm_q, &qdo_full[qs], h * HD, i * 128, b);
             tma_load_3d(smem + Cfg::kOffDO + qs * Cfg::kTileBytes, &tm_do, &qdo_full[qs], h * HD, i * 128, b);
+            tma_load_3d(smem + Cfg::kOffO + qs * Cfg::kTileBytes, &tm_o, &qdo_full[qs], h * HD, i * 128, b);
           }
         }
       }
@@ -225,27 +228,47 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint8_t* ds_row = smem + Cfg::kOffDS + half * 16384 + r * 128;
     const float log2e = 1.4426950408889634f;
     int t = 0;
+    // LSE of this thread's row, fetched one iteration ahead (a 4-byte global load per iteration whose
+    // latency would otherwise sit in front of the exponentials)
+    auto load_lse = [&](int tt) -> float {
+      const int per_item = kvb * qt;
+      const int it_item = blockIdx.x + (tt / per_item) * gridDim.x;
+      if (it_item >= n_items) return 0.f;
+      const int qr = ((tt % per_item) % qt) * 128 + r;
+      if (qr >= p.Nq) return 0.f;
+      return p.lse[(static_cast<long long>(it_item / p.H) * p.H + it_item % p.H) * p.Nq + qr];
+    };
+    float lse_next = load_lse(0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int h = item % p.H, b = item / p.H;
+      (void)h;
+      (void)b;
       for (int j = 0; j < kvb; ++j) {
         const int valid = min(128, p.Nk - j * 128) - half * 64;  // valid columns of this half (may be <= 0)
         for (int i = 0; i < qt; ++i, ++t) {
           const int qrow = i * 128 + r;
-          // per-row statistics: LSE and D = <dO, O>  (rows past Nq: Q/dO tiles are zero-filled, any
-          // finite value keeps their P/dS harmless)
-          float lse2 = 0.f, dsum = 0.f;
-          if (qrow < p.Nq) {
-            lse2 = p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qrow] * log2e;
-            const __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Nq + qrow) * p.ldo + h * HD;
-            const __nv_bfloat16* drow = p.d_o + (static_cast<long long>(b) * p.Nq + qrow) * p.lddo + h * HD;
+          (void)qrow;
+          // per-row statistics: LSE (global, 4 bytes) and D = <dO, O> from the TMA-staged tiles in smem (the
+          // first version read both 128-byte rows from global memory here: that load latency was the
+          // largest stall of the compute warps, ncu r01 attn_bwd v2).  Rows past Nq: the tiles are
+          // zero-filled and any finite LSE keeps their P / dS harmless.
+          const float lse2 = lse_next * log2e;
+          float dsum = 0.f;
+          lse_next = load_lse(t + 1);
+          mbar_wait(&qdo_full[t & 1], (t >> 1) & 1);
+          {
+            const uint32_t o_row = smem_u32(smem + Cfg::kOffO + (t & 1) * Cfg::kTileBytes) + r * Cfg::kRowBytes;
+            const uint32_t d_row = smem_u32(smem + Cfg::kOffDO + (t & 1) * Cfg::kTileBytes) + r * Cfg::kRowBytes;
+            const uint32_t xr = (HD == 64) ? static_cast<uint32_t>(r & 7) : static_cast<uint32_t>((r >> 1) & 3);
 #pragma unroll
             for (int c = 0; c < HD / 8; ++c) {
-              const uint4 a = *reinterpret_cast<const uint4*>(orow + c * 8);
-              const uint4 g = *reinterpret_cast<const uint4*>(drow + c * 8);
-              const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z),
-                           a3 = unpack_bf16x2(a.w);
-              const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z),
-                           g3 = unpack_bf16x2(g.w);
+              const uint32_t off = (static_cast<uint32_t>(c) ^ xr) << 4;
+              const float4 a = lds128(o_row + off);
+              const float4 g = lds128(d_row + off);
+              const float2 a0 = unpack_bf16x2(__float_as_uint(a.x)), a1 = unpack_bf16x2(__float_as_uint(a.y)),
+                           a2 = unpack_bf16x2(__float_as_uint(a.z)), a3 = unpack_bf16x2(__float_as_uint(a.w));
+              const float2 g0 = unpack_bf16x2(__float_as_uint(g.x)), g1 = unpack_bf16x2(__float_as_uint(g.y)),
+                           g2 = unpack_bf16x2(__float_as_uint(g.z)), g3 = unpack_bf16x2(__float_as_uint(g.w));
               dsum += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y +
                       a3.x * g3.x + a3.y * g3.y;
             }
@@ -313,21 +336,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
               const long long ld = which == 0 ? p.lddv : p.lddk;
               __nv_bfloat16* dst = base + (static_cast<long long>(b) * p.Nk + krow) * ld + h * HD;
+              uint32_t v[HD];  // one TMEM round trip per accumulator (the MMA warp waits for this drain)
 #pragma unroll
-              for (int c = 0; c < HD / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + lane_off + 256 + which * 64 + c * 32, v);
-                tmem_ld_wait();
-                if (krow < p.Nk) {
+              for (int c = 0; c < HD / 32; ++c)
+                tmem_ld_32x32b_x32_p(tmem_base + lane_off + 256 + which * 64 + c * 32, v + c * 32);
+              tmem_ld_wait();
+              if (krow < p.Nk) {
 #pragma unroll
-                  for (int q4 = 0; q4 < 4; ++q4) {
-                    uint4 pk;
-                    pk.x = pack_bf16x2(__uint_as_float(v[q4 * 8 + 0]), __uint_as_float(v[q4 * 8 + 1]));
-                    pk.y = pack_bf16x2(__uint_as_float(v[q4 * 8 + 2]), __uint_as_float(v[q4 * 8 + 3]));
-                    pk.z = pack_bf16x2(__uint_as_float(v[q4 * 8 + 4]), __uint_as_float(v[q4 * 8 + 5]));
-                    pk.w = pack_bf16x2(__uint_as_float(v[q4 * 8 + 6]), __uint_as_float(v[q4 * 8 + 7]));
-                    *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = pk;
-                  }
+                for (int q4 = 0; q4 < HD / 8; ++q4) {
+                  uint4 pk;
+                  pk.x = pack_bf16x2(__uint_as_float(v[q4 * 8 + 0]), __uint_as_float(v[q4 * 8 + 1]));
+                  pk.y = pack_bf16x2(__uint_as_float(v[q4 * 8 + 2]), __uint_as_float(v[q4 * 8 + 3]));
+                  pk.z = pack_bf16x2(__uint_as_float(v[q4 * 8 + 4]), __uint_as_float(v[q4 * 8 + 5]));
+                  pk.w = pack_bf16x2(__uint_as_float(v[q4 * 8 + 6]), __uint_as_float(v[q4 * 8 + 7]));
+                  *reinterpret_cast<uint4*>(dst + q4 * 8) = pk;
                 }
               }
             }
@@ -388,7 +410,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 template <int HD>
 static int launch_attn_bwd(const mb_attn_bwd_args* a, cudaStream_t stream) {
   using Cfg = AttnBwdCfg<HD>;
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, to;
   uint32_t box[3] = {(uint32_t)HD, 128u, 1u};
   {
     uint64_t dims[3] = {(uint64_t)a->heads * HD, (uint64_t)a->nq, (uint64_t)a->batch};
@@ -396,6 +418,8 @@ static int launch_attn_bwd(const mb_attn_bwd_args* a, cudaStream_t stream) {
     if (make_tensor_map(&tq, a->q, kTmaBF16, 3, dims, s1, box, Cfg::kSwizzle)) return -1;
     uint64_t s2[2] = {(uint64_t)a->lddo * 2, (uint64_t)a->nq * a->lddo * 2};
     if (make_tensor_map(&tdo, a->d_out, kTmaBF16, 3, dims, s2, box, Cfg::kSwizzle)) return -1;
+    uint64_t s3[2] = {(uint64_t)a->ldo * 2, (uint64_t)a->nq * a->ldo * 2};
+    if (make_tensor_map(&to, a->out, kTmaBF16, 3, dims, s3, box, Cfg::kSwizzle)) return -1;
   }
   {
     uint64_t dims[3] = {(uint64_t)a->heads * HD, (uint64_t)a->nk, (uint64_t)a->batch};
@@ -436,7 +460,7 @@ static int launch_attn_bwd(const mb_attn_bwd_args* a, cudaStream_t stream) {
   }
   const long long items = (long long)p.B * p.H;
   const long long grid = items < sm_count() ? items : sm_count();  // persistent CTAs
-  kern<<<(unsigned)grid, kAttnBwdThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, tdo, p);
+  kern<<<(unsigned)grid, kAttnBwdThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, tdo, to, p);
   MB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
