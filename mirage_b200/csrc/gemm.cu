@@ -38,7 +38,9 @@ static void pick_tiling(long long m, long long n, int splits, int force_bn, int 
   *bn_out = 128;
   *pair_out = false;
   struct Cand { int bn; bool pair; double penalty; };
-  const Cand cands[4] = {{256, true, 1.0}, {128, true, 1.12}, {128, false, 1.35}, {64, false, 1.8}};
+  // penalties measured on B200 at M = 25344 (scripts/check_gemm.py perfpre): a 128-wide pair tile runs at
+  // 0.72-0.75 of the 256-wide one on the same problem; 1-CTA tiles at 0.65 (L2 operand traffic)
+  const Cand cands[4] = {{256, true, 1.0}, {128, true, 1.36}, {128, false, 1.55}, {64, false, 2.0}};
   for (const Cand& c : cands) {
     if (force_bn && c.bn != force_bn) continue;
     if (force_pair == 1 && c.pair) continue;

@@ -441,10 +441,8 @@ def patch_tokens_raw(img, weight, bias, pos_rows, out=None, row_map=None):
 
 def patch_wgrad(img, dtok_bf16):
     """dW[D, 1024] of the 32x32 patch embedding; the bf16 im2col exists only here, never in forward."""
-    Bn, _, H, W = img.shape
-    gh, gw = H // 32, W // 32
-    patches = img.reshape(Bn, gh, 32, gw, 32).permute(0, 1, 3, 2, 4).reshape(Bn * gh * gw, 1024)
-    return wgrad(dtok_bf16, _as_bf16(patches.contiguous()))
+    patches = ops.patchify_cast(img.contiguous().float(), 32, 32)   # one pass: fp32 image -> bf16 [B*N, 1024]
+    return wgrad(dtok_bf16, patches)
 
 
 class _PatchEmbed32(Function):

@@ -102,6 +102,8 @@ class PatchedInputAdapter(nn.Module, _PosEmbMixin):
     def _im2col(self, x):
         B, C, H, W = x.shape
         nh, nw = H // self.P_H, W // self.P_W
+        if x.is_cuda and self.P_W % 8 == 0:
+            return ops.patchify_cast(x.contiguous().float(), self.P_H, self.P_W)   # fused permute + bf16 cast
         a = x.reshape(B, C, nh, self.P_H, nw, self.P_W).permute(0, 2, 4, 1, 3, 5)
         return Fn._as_bf16(a.reshape(B * nh * nw, C * self.P_H * self.P_W).float().contiguous())
 

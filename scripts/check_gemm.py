@@ -271,6 +271,34 @@ def group_maps():
     return ok and untouched
 
 
+def group_perfpre():
+    """cfg-4 sized GEMMs (25344 token rows): 256- vs 128-wide CTA-pair tiles (wave quantisation)."""
+    m = 25344
+    for (n, k, kind) in [(1024, 1024, "res"), (1024, 4096, "res"), (1024, 4096, "dgrad"), (1024, 3072, "dgrad"),
+                         (3072, 1024, "bf16"), (4096, 1024, "gelu")]:
+        for bn in (256, 128):
+            a = mk(m, k)
+            bias = torch.randn(n, device=dev)
+            if kind == "dgrad":
+                w = mk(k, n, scale=k ** -0.5)
+                fn = lambda: ops.gemm(a, w, m=m, n=n, k=k, b_layout=L.MB_MAJOR_MN, block_n=bn, cta_pair=2)
+            elif kind == "res":
+                w = mk(n, k, scale=k ** -0.5)
+                x = torch.randn(m, n, device=dev)
+                fn = lambda: ops.gemm(a, w, m=m, n=n, k=k, bias=bias, residual=x, out=x, block_n=bn, cta_pair=2)
+            elif kind == "gelu":
+                w = mk(n, k, scale=k ** -0.5)
+                pre = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+                fn = lambda: ops.gemm(a, w, m=m, n=n, k=k, bias=bias, gelu=True, aux_out=pre, block_n=bn, cta_pair=2)
+            else:
+                w = mk(n, k, scale=k ** -0.5)
+                fn = lambda: ops.gemm(a, w, m=m, n=n, k=k, bias=bias, block_n=bn, cta_pair=2)
+            ms = _time(fn, iters=20)
+            print(f"[PERF] {kind:6s} m={m} n={n} k={k} pair bn={bn}: {ms * 1e3:.1f} us = {2.0 * m * n * k / ms / 1e9:.0f} TFLOP/s",
+                  flush=True)
+    return True
+
+
 def group_perfepi():
     """Epilogue variants of the encoder's GEMMs at cfg-2 size (the tile loop is identical; only the
     epilogue differs), against the plain bf16 store."""
