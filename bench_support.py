@@ -80,9 +80,29 @@ def build_pretrain_step(size, mods, per_gpu, dev, rank, world):
             resample()
             return g()
 
+        # end-to-end leg: the batch of step k+1 travels host -> device (pinned memory, side stream) while
+        # step k computes, as a prefetching data loader does; each step begins with a device-to-device copy
+        # of the staged batch into the tensors the graph reads
+        side = torch.cuda.Stream(dev)
+        staging = {k: torch.empty_like(v) for k, v in dev_in.items()}
+        state = {"ready": None}
+
+        def prefetch(after):
+            with torch.cuda.stream(side):
+                if after is not None:
+                    side.wait_event(after)
+                for k in staging:
+                    staging[k].copy_(host_in[k], non_blocking=True)
+                state["ready"] = side.record_event()
+
         def gstep_e2e():
+            main = torch.cuda.current_stream(dev)
+            if state["ready"] is None:
+                prefetch(None)
+            main.wait_event(state["ready"])
             for k in x_fixed:
-                x_fixed[k].copy_(host_in[k], non_blocking=True)
+                x_fixed[k].copy_(staging[k], non_blocking=True)
+            prefetch(main.record_event())          # next step's batch, overlapped with this step
             resample()
             loss = g()
             host_loss.copy_(loss.detach().reshape(1), non_blocking=True)

@@ -66,7 +66,7 @@ class MIRAGEWrapper(nn.Module):
         return self.model(x)
 
     @torch.no_grad()
-    def encode_host(self, x: dict, out: torch.Tensor | None = None, chunk: int = 64) -> torch.Tensor:
+    def encode_host(self, x: dict, out: torch.Tensor | None = None, chunk: int = 64, ramp: int = 16) -> torch.Tensor:
         """Batch inference from HOST tensors to a HOST tensor with the copies hidden behind compute.
 
         x: {modality: pinned CPU [B, 1, H, W]}; out: pinned CPU [B, N_all + 1, D] fp32 (allocated when
@@ -75,23 +75,35 @@ class MIRAGEWrapper(nn.Module):
         plus one chunk of PCIe traffic instead of the whole batch's (new: the reference wrapper is a plain
         ``.to(device)`` + forward, hf/mirage_hf.py:670-680).  Returns ``out`` once everything is enqueued;
         the caller synchronises (``torch.cuda.current_stream().synchronize()``) before reading it.
+        The first and the last chunk are short (``ramp`` images): what cannot overlap is the first
+        chunk's H2D and the last chunk's D2H, so those are kept small.
         """
         dev = self.device
         names = list(x.keys())
         B = x[names[0]].shape[0]
         chunk = max(1, min(chunk, B))
+        # chunk boundaries: [ramp] + equal middle chunks + [ramp]
+        if ramp > 0 and B >= 2 * ramp + chunk:
+            mid = B - 2 * ramp
+            n_mid = (mid + chunk - 1) // chunk
+            sizes = [ramp] + [mid // n_mid + (1 if i < mid % n_mid else 0) for i in range(n_mid)] + [ramp]
+        else:
+            sizes = [chunk] * (B // chunk) + ([B % chunk] if B % chunk else [])
+        bounds = [0]
+        for sz in sizes:
+            bounds.append(bounds[-1] + sz)
         main = torch.cuda.current_stream(dev)
         if not hasattr(self, "_pipe_streams"):
             self._pipe_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
         s_in, s_out = self._pipe_streams
         s_in.wait_stream(main)
         s_out.wait_stream(main)
-        n_chunks = (B + chunk - 1) // chunk
+        n_chunks = len(sizes)
         staged, ev_in, ev_free = [None, None], [None, None], [None, None]
         outs, ev_done = [None, None], [None, None]
 
         def load(i):
-            b0, b1 = i * chunk, min(B, (i + 1) * chunk)
+            b0, b1 = bounds[i], bounds[i + 1]
             slot = i & 1
             with torch.cuda.stream(s_in):
                 if ev_free[slot] is not None:
@@ -112,7 +124,7 @@ class MIRAGEWrapper(nn.Module):
             ev_tok = main.record_event()
             if out is None:
                 out = torch.empty((B,) + tuple(tok.shape[1:]), dtype=tok.dtype).pin_memory()
-            b0, b1 = i * chunk, min(B, (i + 1) * chunk)
+            b0, b1 = bounds[i], bounds[i + 1]
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_tok)
                 out[b0:b1].copy_(tok, non_blocking=True)
