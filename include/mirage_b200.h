@@ -95,6 +95,8 @@ typedef struct mb_gemm_args {
   int64_t out_row_period, out_row_stride, out_row_offset; /* 0,0,0 = identity row map */
   int32_t up_channels, up_ph, up_pw, up_gh, up_gw;        /* MB_EPI_UNPATCH only */
   int32_t cta_pair; /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA pairs (cta_group::2, 256 rows) */
+  float* colsum_out; /* f32 [N] or NULL: ACCUMULATES the column sums of the stored output (the bias gradient
+                        of the layer whose data gradient this GEMM produces); MB_EPI_DGELU with bf16 out only */
 } mb_gemm_args;
 
 int mb_gemm(const mb_gemm_args* args, void* stream);

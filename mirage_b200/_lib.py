@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("up_channels", C.c_int32), ("up_ph", C.c_int32), ("up_pw", C.c_int32),
         ("up_gh", C.c_int32), ("up_gw", C.c_int32),
         ("cta_pair", C.c_int32),
+        ("colsum_out", C.c_void_p),
     ]
 
 

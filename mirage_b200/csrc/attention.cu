@@ -17,7 +17,7 @@
 //                    O_g += P_g V_j       (TS: P_g read from TMEM as the A operand, V MN-major in smem)
 //   warps 4-11   softmax group 0: TWO threads per query row (warps 4-7 own key columns [0,64) of the
 //   warps 12-19  softmax group 1   block, warps 8-11 columns [64,128)); the two halves exchange their
-//                row maxima through smem + a named barrier, everything else is thread-private.  Four
+//                row maxima through smem + a 64-thread named barrier (per 32 rows), everything else is thread-private.  Four
 //                softmax warps per SM sub-partition instead of two: the first layout (one thread per
 //                row, 128 values in registers) left the MUFU idle 2/3 of the time for lack of warps to
 //                switch to (ncu r01 v5: issue 38 %, XU 36 %, top stall "wait")
@@ -530,10 +530,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int t = 0; t < kMaxTail; ++t) mx_loc = fmaxf(mx_loc, s_tail[t]);  // -inf when unused / half 1
           }
         }
-        // exchange (double-buffered by block parity; one named barrier per block and group)
+        // exchange (double-buffered by block parity; one 64-thread named barrier per block and row quarter)
         float* xc = xchg + ((cnt & 1) * 4 + g * 2) * 128;
         xc[hf * 128 + r] = mx_loc;
-        named_bar_sync(1 + g, 256);
+        named_bar_sync(1 + g * 4 + quarter, 64);  // just the two warps that share these 32 rows
         const float mx_row = fmaxf(mx_loc, xc[(hf ^ 1) * 128 + r]);
 
         float alpha = 1.f;

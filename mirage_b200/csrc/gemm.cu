@@ -88,6 +88,11 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
   MB_REQUIRE((a->epilogue & ~(MB_EPI_GELU | MB_EPI_DGELU | MB_EPI_ATOMIC | MB_EPI_UNPATCH)) == 0,
              "mb_gemm: unknown epilogue bits 0x%x", a->epilogue);
   if (a->residual) MB_REQUIRE(a->ld_res % 4 == 0, "mb_gemm: ld_res must be a multiple of 4");
+  MB_REQUIRE(a->colsum_out == nullptr ||
+                 ((a->epilogue & MB_EPI_DGELU) && a->out_dtype == MB_BF16 && !a->residual &&
+                  !(a->epilogue & (MB_EPI_ATOMIC | MB_EPI_UNPATCH | MB_EPI_GELU)) && a->out_row_period == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->colsum_out) & 15) == 0),
+             "mb_gemm: colsum_out needs the plain MB_EPI_DGELU epilogue with a bf16 output and a 16-byte aligned buffer");
   if (a->aux_in || a->aux_out) MB_REQUIRE(a->ld_aux % 8 == 0, "mb_gemm: ld_aux must be a multiple of 8");
   const bool tf32 = (a->in_dtype == MB_F32);
   const int esize = tf32 ? 4 : 2;
@@ -115,6 +120,7 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
   p.residual = a->residual;
   p.aux_in = reinterpret_cast<const __nv_bfloat16*>(a->aux_in);
   p.aux_out = reinterpret_cast<__nv_bfloat16*>(a->aux_out);
+  p.colsum_out = a->colsum_out;
   p.M = (int)a->m;
   p.N = (int)a->n;
   p.K = (int)a->k;

@@ -35,6 +35,7 @@ struct GemmDev {
   const float* residual;
   const __nv_bfloat16* aux_in;
   __nv_bfloat16* aux_out;
+  float* colsum_out;  // EPI_DGELU: column sums of the output accumulate here (bias gradient)
   int M, N, K;
   long long ldc, ld_res, ld_aux;
   int res_period;
@@ -310,6 +311,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
         }
       }
       const bool atomic = (MODE == EPI_F32) && (p.epilogue & MB_EPI_ATOMIC);
+      [[maybe_unused]] float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;  // EPI_DGELU: column sums of this thread's rows
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int row = row_base + it * 4 + sub;
@@ -330,6 +332,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
           gelu_fast_grad2(h0.x, h0.y);
           gelu_fast_grad2(h1.x, h1.y);
           f0 *= h0.x; f1 *= h0.y; f2 *= h1.x; f3 *= h1.y;
+          if (ok) { cs0 += f0; cs1 += f1; cs2 += f2; cs3 += f3; }
         }
         if constexpr (MODE == EPI_RES) {
           f0 += cur.res[it].x; f1 += cur.res[it].y; f2 += cur.res[it].z; f3 += cur.res[it].w;
@@ -348,6 +351,15 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
             pk.y = pack_bf16x2(f2, f3);
             *reinterpret_cast<uint2*>(optr + it * ostep) = pk;
           }
+        }
+      }
+      if constexpr (MODE == EPI_DGELU) {
+        if (p.colsum_out != nullptr) {  // fold the 4 row groups (lanes j4, j4+8, j4+16, j4+24), one vector reduction
+          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+          cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
+          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+          cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
+          if (sub == 0 && col_ok) red_add_v4(p.colsum_out + col, cs0, cs1, cs2, cs3);
         }
       }
       cur = nxt;

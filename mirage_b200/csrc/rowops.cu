@@ -194,8 +194,8 @@ colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out0, fl
 // ------------------------------------------------------------------------------------------
 template <bool IN_BF16>
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const void* __restrict__ a, float* __restrict__ part, long long M, int N,
-                      long long lda, int rows_per_block, int cpb) {
+colsum_partial_kernel(const void* __restrict__ a, float* __restrict__ part, float* __restrict__ direct,
+                      long long M, int N, long long lda, int rows_per_block, int cpb) {
   constexpr int EPC = IN_BF16 ? 8 : 4;  // elements per 16-byte chunk
   __shared__ float sm[256 * 8];
   const int lanes = 256 / cpb;
@@ -245,12 +245,21 @@ colsum_partial_kernel(const void* __restrict__ a, float* __restrict__ part, long
   for (int e = 0; e < EPC; ++e) sm[(ly * EPC + e) * cpb + cx] = acc[e];
   __syncthreads();
   if (ly == 0 && col < N) {
-    float* o = part + (long long)blockIdx.x * N + col;
+    float t[EPC];
 #pragma unroll
     for (int e = 0; e < EPC; ++e) {
-      float t = 0.f;
-      for (int l = 0; l < lanes; ++l) t += sm[(l * EPC + e) * cpb + cx];
-      o[e] = t;
+      t[e] = 0.f;
+      for (int l = 0; l < lanes; ++l) t[e] += sm[(l * EPC + e) * cpb + cx];
+    }
+    if (direct != nullptr) {
+      // accumulate mode (gradient buckets): one vector reduction per 4 columns straight into the
+      // destination, no partial buffer and no second kernel
+#pragma unroll
+      for (int e = 0; e < EPC; e += 4) red_add_v4(direct + col + e, t[e], t[e + 1], t[e + 2], t[e + 3]);
+    } else {
+      float* o = part + (long long)blockIdx.x * N + col;
+#pragma unroll
+      for (int e = 0; e < EPC; ++e) o[e] = t[e];
     }
   }
 }
@@ -461,11 +470,14 @@ int mb_colsum(const void* a, int32_t a_dtype, float* out, int32_t accumulate, vo
   colsum_plan(rows, cols, esize, &cpb, &gy, &rpb, &gx);
   dim3 grid((unsigned)gx, (unsigned)gy);
   float* part = reinterpret_cast<float*>(workspace);
+  // accumulate into a 16-byte aligned destination: single kernel with vector reductions
+  float* direct = (accumulate && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? out : nullptr;
   if (a_dtype == MB_BF16)
-    colsum_partial_kernel<true><<<grid, 256, 0, st>>>(a, part, rows, (int)cols, lda, rpb, cpb);
+    colsum_partial_kernel<true><<<grid, 256, 0, st>>>(a, part, direct, rows, (int)cols, lda, rpb, cpb);
   else
-    colsum_partial_kernel<false><<<grid, 256, 0, st>>>(a, part, rows, (int)cols, lda, rpb, cpb);
+    colsum_partial_kernel<false><<<grid, 256, 0, st>>>(a, part, direct, rows, (int)cols, lda, rpb, cpb);
   MB_CHECK_CUDA(cudaGetLastError());
+  if (direct != nullptr) return 0;
   colsum_final_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 32), 0, st>>>(
       part, out, nullptr, gx, (int)cols, (int)cols, accumulate);
   MB_CHECK_CUDA(cudaGetLastError());

@@ -138,12 +138,15 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, into: Optional[torch.Tensor] = None
     return out
 
 
-def dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, *, out_dtype=torch.bfloat16, dgelu_aux=None) -> torch.Tensor:
-    """dx[T, k_in] = dy[T, n_out] W[n_out, k_in]  (W consumed MN-major: no transposed copy)."""
+def dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, *, out_dtype=torch.bfloat16, dgelu_aux=None,
+          colsum_out=None) -> torch.Tensor:
+    """dx[T, k_in] = dy[T, n_out] W[n_out, k_in]  (W consumed MN-major: no transposed copy).
+    ``colsum_out`` (with ``dgelu_aux``): fp32 [k_in] buffer that ACCUMULATES the column sums of dx --
+    the bias gradient of the layer below, computed in the epilogue instead of a separate pass."""
     T, n_out = dy.shape
     k_in = w_bf16.shape[1]
     return ops.gemm(dy, w_bf16, m=T, n=k_in, k=n_out, b_layout=L.MB_MAJOR_MN, out_dtype=out_dtype,
-                    dgelu_aux=dgelu_aux)
+                    dgelu_aux=dgelu_aux, colsum_out=colsum_out)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -358,9 +361,10 @@ class _Block(Function):
         # MLP branch
         d_fc2_w = wgrad(dyb, g, into=tg[10])
         d_fc2_b = ops.colsum(dyb, into=tg[11])
-        dpre = dgrad(dyb, bf16_weight(fc2_w), dgelu_aux=pre)
+        # fc1's bias gradient = column sums of dpre, accumulated by the dgrad epilogue that produces dpre
+        d_fc1_b = tg[9] if tg[9] is not None else torch.zeros(fc1_w.shape[0], dtype=torch.float32, device=x.device)
+        dpre = dgrad(dyb, bf16_weight(fc2_w), dgelu_aux=pre, colsum_out=d_fc1_b)
         d_fc1_w = wgrad(dpre, h2, into=tg[8])
-        d_fc1_b = ops.colsum(dpre, into=tg[9])
         dh2 = dgrad(dpre, bf16_weight(fc1_w))
         dx1, dx1b, d_n2w, d_n2b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2, want_bf16=True,
                                                     dw_into=tg[6], db_into=tg[7])

@@ -75,7 +75,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int,
          atomic: bool = False, k_splits: int = 1, block_n: int = 0,
          img_hw: tuple[int, int] | None = None,
          out_row_map: tuple[int, int, int] | None = None,
-         unpatch: tuple[int, int, int, int, int] | None = None, cta_pair: int = 0) -> torch.Tensor:
+         unpatch: tuple[int, int, int, int, int] | None = None, cta_pair: int = 0,
+         colsum_out: torch.Tensor | None = None) -> torch.Tensor:
     """out[m, n] = epilogue(A * B^T); see ``mb_gemm`` in include/mirage_b200.h for the contract.
 
     ``a`` / ``b`` are 2-D (or, for MB_A_PATCH32, the [B,1,H,W] fp32 image batch) with unit stride in
@@ -130,6 +131,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int,
     args.k_splits = k_splits
     args.block_n = block_n
     args.cta_pair = cta_pair
+    args.colsum_out = _ptr(colsum_out)
     if out_row_map is not None:
         args.out_row_period, args.out_row_stride, args.out_row_offset = out_row_map
     if unpatch is not None:

@@ -117,6 +117,12 @@ def group_rowops():
         ok &= report(f"colsum f32 {rows}x{cols}", ops.colsum(a)[None], a.double().sum(0).float()[None], tol=1e-4)
         ab = a.bfloat16()
         ok &= report(f"colsum bf16 {rows}x{cols}", ops.colsum(ab)[None], ab.double().sum(0).float()[None], tol=1e-4)
+    acc = torch.ones(1024, device=dev)
+    a = torch.randn(25344, 1024, device=dev).bfloat16()
+    ops.colsum(a, into=acc)
+    ops.colsum(a, into=acc)
+    ok &= report("colsum accumulate (single-kernel vector reductions)", acc[None],
+                 (1 + 2 * a.double().sum(0)).float()[None], tol=1e-4)
     big = torch.randn(4096, 3072, device=dev).bfloat16()
     ok &= report("colsum bf16 column slice (ld 3072)", ops.colsum(big[:, 1024:2048])[None],
                  big[:, 1024:2048].double().sum(0).float()[None], tol=1e-4)

@@ -98,6 +98,17 @@ def group_epilogue():
     hf = h.float().requires_grad_(True)
     g = torch.autograd.grad(torch.nn.functional.gelu(hf).sum(), hf)[0]
     ok &= report("dgelu", out, base * g)
+    # dgrad through the GELU with the bias gradient (column sums of the result) from the epilogue
+    for (m2, n2, k2) in [(1000, 512, 256), (25344, 4096, 1024)]:
+        dy, w2 = mk(m2, k2), mk(k2, n2, scale=k2 ** -0.5)
+        h2 = mk(m2, n2)
+        cs = torch.full((n2,), 3.0, device=dev)
+        out2 = ops.gemm(dy, w2, m=m2, n=n2, k=k2, b_layout=L.MB_MAJOR_MN, dgelu_aux=h2, colsum_out=cs)
+        hf2 = h2.float().requires_grad_(True)
+        g2 = torch.autograd.grad(torch.nn.functional.gelu(hf2).sum(), hf2)[0]
+        ref2 = (dy.float() @ w2.float()) * g2
+        ok &= report(f"dgelu + colsum: output m={m2}", out2, ref2)
+        ok &= report(f"dgelu + colsum: column sums m={m2}", cs[None], (3.0 + ref2.double().sum(0)).float()[None], tol=2e-3)
     return ok
 
 
