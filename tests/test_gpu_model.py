@@ -183,3 +183,54 @@ def test_cls_finetune_step_vs_reference_golden(pool):
         p = dict(m.named_parameters())[k]
         assert p.grad is not None, k
         assert abs(p.grad.norm().item() - n) <= 5e-2 * n, (k, p.grad.norm().item(), n)
+
+
+def _light_model(mods, size, image=512):
+    """model_factory-style MIRAGELight (no masking) over the given modalities."""
+    import argparse
+    from mirage_b200.input_adapters import PatchedInputAdapter, SemSegInputAdapter
+    from mirage_b200.model import MIRAGELight
+    dim, depth, heads = {"tiny": (128, 2, 2), "base": (768, 12, 12)}[size]
+    a = argparse.Namespace()
+    a.in_domains = list(mods)
+    a.patch_size = {d: ((8, 8) if d == "bscanlayermap" else (32, 32)) for d in mods}
+    a.input_size = {d: ((image // 4, image // 4) if d == "bscanlayermap" else (image, image)) for d in mods}
+    a.grid_sizes = {d: [image // 32, image // 32] for d in mods}
+    ins = {}
+    for d in mods:
+        if d == "bscanlayermap":
+            ins[d] = SemSegInputAdapter(num_classes=13, stride_level=1, patch_size_full=(8, 8),
+                                        image_size=a.input_size[d], dim_class_emb=64, interpolate_class_emb=False)
+        else:
+            ins[d] = PatchedInputAdapter(num_channels=1, stride_level=1, patch_size_full=(32, 32),
+                                         image_size=a.input_size[d])
+    m = MIRAGELight(a, input_adapters=ins, output_adapters=None, num_global_tokens=1, dim_tokens=dim,
+                    depth=depth, num_heads=heads, drop_path_rate=0.0)
+    return m, depth, heads
+
+
+@pytest.mark.parametrize("mods,size,batch,image", [
+    (["bscan", "slo", "bscanlayermap"], "base", 3, 512),   # N = 769: three query-tile pairs + global token
+    (["bscan"], "base", 5, 512),                            # N = 257, odd batch
+    (["bscan", "slo"], "tiny", 2, 1024),                    # N = 2049 (segmentation-size input, 1024 x 1024)
+    (["slo"], "tiny", 1, 512),
+])
+def test_light_encoder_shapes_vs_oracle(mods, size, batch, image):
+    """Sequence lengths / modality mixes beyond the two bench configs, incl. return_all_layers."""
+    from oracle import mirage_oracle as O
+    dev = torch.device("cuda:0")
+    m, depth, heads = _light_model(mods, size, image)
+    sd = load_synth(m, seed=4)
+    m = m.to(dev).eval()
+    x = synth_images(batch, mods, seed=12, size=image)
+    with torch.no_grad():
+        out = m({k: v.to(dev) for k, v in x.items()})
+        ref = O.light_forward(x, sd, depth, heads)
+        assert out.shape == ref.shape
+        assert_parity(out, ref, f"light {mods} {size} B={batch} {image}")
+        if size == "tiny":
+            layers = m({k: v.to(dev) for k, v in x.items()}, return_all_layers=True)
+            refs = O.light_forward(x, sd, depth, heads, return_all_layers=True)
+            assert len(layers) == len(refs)
+            for a_, b_ in zip(layers, refs):
+                assert_parity(a_, b_, "return_all_layers")
