@@ -776,6 +776,97 @@ attn_tail_rows_kernel(const AttnDev p) {
   }
 }
 
+// Same computation for FOUR consecutive heads per CTA: a token's K (or V) row of four heads is 512
+// contiguous bytes, read by one warp with one 16-byte load per lane, instead of four CTAs each pulling
+// a 128-byte piece of the same DRAM page at different times (ncu r01: 3.9 TB/s for the per-head kernel).
+//   lane l: head l >> 3 of the group, dims [8 (l & 7), +8);  warp w: keys w, w+4, ...
+template <int HD>
+__global__ void __launch_bounds__(kTailThreads)
+attn_tail_rows4_kernel(const AttnDev p) {
+  static_assert(HD == 64, "tail rows are only peeled for head_dim 64");
+  extern __shared__ float tsm[];
+  float* s_p = tsm;                        // [4][Nk_pad]
+  const int nk_pad = (p.Nk + 3) & ~3;
+  float* s_q = s_p + 4 * nk_pad;           // [4][64]   q * scale * log2(e)
+  float* s_o = s_q + 4 * HD;               // [4 warps][4 heads * 64]
+  float* s_ml = s_o + 4 * 4 * HD;          // [4] max, [4] sum
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hh = lane >> 3, c8 = (lane & 7) * 8;
+  const int groups = p.H / 4;
+  const int h0 = (blockIdx.x % groups) * 4, b = blockIdx.x / groups;
+  const __nv_bfloat16* kbase = p.k + static_cast<long long>(b) * p.Nk * p.ldk + h0 * HD + lane * 8;
+  const __nv_bfloat16* vbase = p.v + static_cast<long long>(b) * p.Nk * p.ldv + h0 * HD + lane * 8;
+
+  for (int qrow = p.Nq_main; qrow < p.Nq; ++qrow) {
+    __syncthreads();
+    for (int i = tid; i < 4 * HD; i += kTailThreads)
+      s_q[i] = __bfloat162float(p.q[(static_cast<long long>(b) * p.Nq + qrow) * p.ldq + h0 * HD + i]) * p.scale_log2;
+    __syncthreads();
+    float qf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qf[i] = s_q[hh * HD + c8 + i];
+    // ---- scores
+#pragma unroll 4
+    for (int key = warp; key < p.Nk; key += 4) {
+      const uint4 kv4 = __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<long long>(key) * p.ldk));
+      const float2 k0 = unpack_bf16x2(kv4.x), k1 = unpack_bf16x2(kv4.y), k2 = unpack_bf16x2(kv4.z),
+                   k3 = unpack_bf16x2(kv4.w);
+      float a = qf[0] * k0.x + qf[1] * k0.y + qf[2] * k1.x + qf[3] * k1.y + qf[4] * k2.x + qf[5] * k2.y +
+                qf[6] * k3.x + qf[7] * k3.y;
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      if ((lane & 7) == 0) s_p[hh * nk_pad + key] = a;
+    }
+    __syncthreads();
+    // ---- softmax of head `warp`
+    {
+      float* pr = s_p + warp * nk_pad;
+      float mx = -INFINITY;
+      for (int key = lane; key < p.Nk; key += 32) mx = fmaxf(mx, pr[key]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int key = lane; key < p.Nk; key += 32) {
+        const float e = fast_exp2(pr[key] - mx);
+        pr[key] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        s_ml[warp] = mx;
+        s_ml[4 + warp] = sum;
+      }
+    }
+    __syncthreads();
+    // ---- P V
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+    for (int key = warp; key < p.Nk; key += 4) {
+      const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<long long>(key) * p.ldv));
+      const float e = s_p[hh * nk_pad + key];
+      const float2 v0 = unpack_bf16x2(vv.x), v1 = unpack_bf16x2(vv.y), v2 = unpack_bf16x2(vv.z),
+                   v3 = unpack_bf16x2(vv.w);
+      acc[0] = fmaf(e, v0.x, acc[0]); acc[1] = fmaf(e, v0.y, acc[1]);
+      acc[2] = fmaf(e, v1.x, acc[2]); acc[3] = fmaf(e, v1.y, acc[3]);
+      acc[4] = fmaf(e, v2.x, acc[4]); acc[5] = fmaf(e, v2.y, acc[5]);
+      acc[6] = fmaf(e, v3.x, acc[6]); acc[7] = fmaf(e, v3.y, acc[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_o[warp * 4 * HD + lane * 8 + i] = acc[i];
+    __syncthreads();
+    for (int i = tid; i < 4 * HD; i += kTailThreads) {
+      const int head = i / HD;
+      const float o = (s_o[i] + s_o[4 * HD + i] + s_o[8 * HD + i] + s_o[12 * HD + i]) / s_ml[4 + head];
+      p.out[(static_cast<long long>(b) * p.Nq + qrow) * p.ldo + h0 * HD + i] = __float2bfloat16(o);
+    }
+    if (tid < 4 && p.lse != nullptr)
+      p.lse[(static_cast<long long>(b) * p.H + h0 + tid) * p.Nq + qrow] =
+          (s_ml[tid] + log2f(s_ml[4 + tid])) * 0.6931471805599453f;
+  }
+}
+
 template <int HD, int POLY>
 static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
   using Cfg = AttnCfg<HD>;
@@ -843,8 +934,22 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
   kern<<<(unsigned)grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   MB_CHECK_CUDA(cudaGetLastError());
   if constexpr (HD == 64) {
-    if (p.Nq_main < p.Nq)
-      attn_tail_rows_kernel<HD><<<(unsigned)(p.B * p.H), kTailThreads, 0, stream>>>(p);
+    if (p.Nq_main < p.Nq) {
+      // four heads per CTA read 512-byte row segments (better DRAM locality) but give 4x fewer CTAs: only
+      // when that still fills the machine several times over
+      if (p.H % 4 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && (long long)p.B * (p.H / 4) >= 4ll * sm_count()) {
+        const size_t tsmem = (size_t)(4 * ((p.Nk + 3) & ~3) + 4 * HD + 16 * HD + 8) * sizeof(float);
+        static bool tail_configured = false;
+        if (!tail_configured) {
+          MB_CHECK_CUDA(cudaFuncSetAttribute(attn_tail_rows4_kernel<HD>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 + 16 * 1024));
+          tail_configured = true;
+        }
+        attn_tail_rows4_kernel<HD><<<(unsigned)(p.B * (p.H / 4)), kTailThreads, tsmem, stream>>>(p);
+      } else {
+        attn_tail_rows_kernel<HD><<<(unsigned)(p.B * p.H), kTailThreads, 0, stream>>>(p);
+      }
+    }
     MB_CHECK_CUDA(cudaGetLastError());
   }
   return 0;

@@ -74,6 +74,9 @@ def group_attn64():
     ok &= attn_case(40, 16, 257, 257, 64)
     ok &= attn_case(64, 16, 99, 99, 64)
     ok &= attn_case(20, 16, 514, 514, 64)                  # two peeled rows: separate tail kernel
+    # enough (batch, head-group) CTAs for the four-heads-per-CTA tail kernel
+    ok &= attn_case(160, 16, 257, 257, 64)
+    ok &= attn_case(200, 12, 130, 130, 64)
     return ok
 
 
