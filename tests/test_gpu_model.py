@@ -56,7 +56,10 @@ def test_encoder_full_batch_properties():
     # identical images give identical tokens wherever they sit in the batch (bitwise: same kernels,
     # same tile decomposition along K; rows do not interact)
     assert torch.equal(big[:8], big[8:16])
-    assert_parity(big[:8], small, "batch 256 vs batch 8", max_rel=1e-5, cos=0.99999)
+    # ... and agree with the same images run as a batch of 8 up to bf16 rounding: the kernel variant may
+    # depend on the batch (e.g. the four-heads-per-CTA tail-row kernel needs enough CTAs), which changes
+    # fp32 summation order, hence an occasional bf16 rounding flip that 24 layers carry along
+    assert_parity(big[:8], small, "batch 256 vs batch 8", max_rel=1e-2, cos=0.9999)
 
 
 @pytest.mark.parametrize("size,batch", [("tiny", 3), ("base", 2)])
