@@ -133,9 +133,9 @@ class MIRAGEModel(nn.Module):
         alphas = [alphas] * len(input_tokens) if isinstance(alphas, float) else alphas
         if sample_tasks_uniformly:
             conc = self.sample_alphas(B, len(input_tokens), alphas=alphas)
-            share = Dirichlet(conc).sample().to(device)
+            share = self._to_device_async(Dirichlet(conc).sample(), device)
         else:
-            share = Dirichlet(torch.Tensor(alphas)).sample((B,)).to(device)
+            share = self._to_device_async(Dirichlet(torch.Tensor(alphas)).sample((B,)), device)
         per_task = (share * num_encoded_tokens).round().long()
 
         masks = []
@@ -157,6 +157,31 @@ class MIRAGEModel(nn.Module):
         mask_all = torch.gather(mask_all, dim=1, index=ids_restore)
         task_masks = dict(zip(input_tokens.keys(), torch.split(mask_all, counts, dim=1)))
         return task_masks, ids_keep, ids_restore
+
+    def _to_device_async(self, t: Tensor, device) -> Tensor:
+        """Host -> device copy of the (CPU-sampled, as in the reference) Dirichlet shares without stalling
+        the host: a pageable ``.to(device)`` makes the CPU wait until the GPU has drained everything queued
+        before it, i.e. the previous training step, so step k+1 could not be enqueued while step k runs.
+        The values, and therefore the masks, are unchanged.  A small ring of pinned staging buffers is
+        reused; a slot is recycled only after its previous copy has completed."""
+        if torch.device(device).type != 'cuda':
+            return t.to(device)
+        ring = getattr(self, '_share_ring', None)
+        if ring is None or ring['shape'] != tuple(t.shape) or ring['dtype'] != t.dtype:
+            ring = {'shape': tuple(t.shape), 'dtype': t.dtype, 'i': 0,
+                    'buf': [torch.empty(t.shape, dtype=t.dtype).pin_memory() for _ in range(4)],
+                    'ev': [None] * 4}
+            self._share_ring = ring
+        i = ring['i']
+        ring['i'] = (i + 1) % 4
+        if ring['ev'][i] is not None:
+            ring['ev'][i].synchronize()
+        ring['buf'][i].copy_(t)
+        out = ring['buf'][i].to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        ring['ev'][i] = ev
+        return out
 
     @staticmethod
     def make_mask(N_H, N_W, xy_idxs, full_tasks=[], indicate_visible=True, flatten=True, device='cuda'):
