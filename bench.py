@@ -419,9 +419,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel eagerly")
-    # 55 / 18 images x 513 tokens = 111 / 37 row tiles of 256: every GEMM of the chunk is a whole number of
-    # waves on 74 CTA pairs (4, 12 or 16 column tiles), so chunking costs no wave quantisation
-    ap.add_argument("--e2e-chunk", type=int, default=55, help="images per pipelined chunk of the e2e leg")
+    # e2e leg: [ramp, everything else, ramp] images; 18 / 220 images x 513 tokens are whole numbers of 256-row
+    # tiles per wave, and three chunks keep the per-kernel ramp-up cost (195 launches per chunk) small
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="images per middle chunk of the e2e leg (0 = one)")
     ap.add_argument("--e2e-ramp", type=int, default=18, help="images in the first and last (short) chunk")
     args = ap.parse_args()
     if args.impl == "reference":

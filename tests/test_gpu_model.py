@@ -151,8 +151,8 @@ def test_encode_host_pipeline_matches_forward():
     x = {k: v.pin_memory() for k, v in synth_images(7, ["bscan", "slo"], seed=9).items()}
     with torch.no_grad():
         ref = m({k: v.to(dev) for k, v in x.items()})
-    for chunk in (2, 3, 7, 64):
-        out = m.encode_host(x, chunk=chunk)
+    for chunk, ramp in ((2, 18), (3, 18), (7, 18), (64, 18), (0, 18), (0, 1), (2, 1)):
+        out = m.encode_host(x, chunk=chunk, ramp=ramp)
         torch.cuda.synchronize()
         assert out.shape == ref.shape and out.is_pinned()
         assert_parity(out, ref, f"encode_host chunk={chunk}", max_rel=1e-5, cos=0.99999)
