@@ -70,3 +70,32 @@ def test_bucketed_allreduce_matches_single_process():
         assert torch.allclose(got[n], ref[n], rtol=1e-5, atol=1e-7), n
     total = torch.sqrt(sum((v ** 2).sum() for v in ref.values())).item()
     assert abs(ret["norm"] - total) <= 1e-5 * total
+
+
+def test_bucket_views_are_128_byte_aligned():
+    """Every gradient view starts on a 128-byte boundary of its bucket (the CUDA kernels write them with
+    16-byte vector stores / vector reductions) -- also behind a 5-element bias -- and zero_grad() keeps
+    the views in place."""
+    from mirage_b200.ddp import GradBucketAllReduce
+    torch.manual_seed(1)
+    model = nn.Sequential(nn.Linear(7, 5), nn.Linear(5, 33), nn.LayerNorm(33), nn.Linear(33, 3))
+    ddp = GradBucketAllReduce(model, bucket_mb=0.001)
+    assert len(ddp.buckets) >= 2
+    seen = set()
+    for b in ddp.buckets:
+        base = b.flat.data_ptr()
+        for p in b.params:
+            off = p.grad.data_ptr() - base
+            assert off % 128 == 0 and 0 <= off < b.flat.numel() * 4, (tuple(p.shape), off)
+            assert p.grad.shape == p.shape and p.grad.is_contiguous()
+            seen.add(id(p))
+    assert seen == {id(p) for p in model.parameters()}
+    ptrs = [p.grad.data_ptr() for p in model.parameters()]
+    model(torch.randn(4, 7)).sum().backward()
+    ddp.finish()
+    g0 = [p.grad.clone() for p in model.parameters()]
+    assert all(float(g.abs().sum()) > 0 for g in g0[:2])
+    ddp.zero_grad()
+    assert ptrs == [p.grad.data_ptr() for p in model.parameters()]
+    assert all(float(p.grad.abs().sum()) == 0.0 for p in model.parameters())
+    assert ddp.num_params == sum(p.numel() for p in model.parameters())
