@@ -195,6 +195,107 @@ int mb_fill_global_rows(const float* global_tokens, float* out, int64_t batch, i
                         int64_t row_offset, int64_t n_global, int64_t dim, void* stream);
 int mb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 
+/* LayerNorm + token mean-pool of the classification wrappers:
+ *   pooled[b, c] = mean over t in [row_begin, row_end) of LayerNorm(x[b, t, :])[c]
+ * mirage_wrapper.py:217-224 (MIRAGEClsGlobal.forward / .pool), :230-233 (CLS), :236-244 (TokenMix: two
+ * calls writing the two halves of a [B, 2*dim] output through ld_pooled).
+ * x f32 [B, n_tokens, dim] contiguous; pooled f32 [B, ld_pooled]; xhat_mean f32 [B, dim], mean / rstd
+ * f32 [B, n_tokens] (entries of the pooled rows are written) are saved for the backward pass.
+ * workspace: mb_ln_meanpool_workspace(batch, dim) bytes.  dim % 128 == 0, dim <= 1024. */
+int64_t mb_ln_meanpool_workspace(int64_t batch, int64_t dim);
+int mb_ln_meanpool_fwd(const float* x, const float* gamma, const float* beta, float* pooled, int64_t ld_pooled,
+                       float* xhat_mean, float* mean, float* rstd, void* workspace, int64_t batch,
+                       int64_t n_tokens, int64_t dim, int64_t row_begin, int64_t row_end, float eps,
+                       void* stream);
+/* Backward: dx f32 [B, n_tokens, dim] receives the gradient of the pooled rows (rows outside the range are
+ * zeroed when zero_outside != 0, left untouched otherwise -- the second call of TokenMix); d_gamma / d_beta
+ * f32 [dim] overwritten or accumulated. */
+int mb_ln_meanpool_bwd(const float* d_pooled, int64_t ld_dp, const float* x, const float* gamma,
+                       const float* mean, const float* rstd, const float* xhat_mean, float* dx,
+                       float* d_gamma, float* d_beta, int32_t accumulate, int32_t zero_outside,
+                       int64_t batch, int64_t n_tokens, int64_t dim, int64_t row_begin, int64_t row_end,
+                       void* stream);
+
+/* ---------------------------------------------------------------- optimizer step (8(f1)) ---- */
+/* Fused AdamW over parameter groups + global gradient norm / clip / skip + in-place refresh of the bf16
+ * weight shadows the GEMMs read.  Replaces, per training step:
+ *   optim.AdamW.step over get_parameter_groups()        mutils/optim_factory.py:33-92, :171-172
+ *   per-step lr / weight-decay assignment                run_pretraining.py:683-688  (hyper table)
+ *   unscale_/clip_grad_norm_/get_grad_norm_/skip_grad    mutils/native_scaler.py:16-37, :46-61
+ * Arithmetic is torch.optim.AdamW's (decoupled decay, bias-corrected, fp32 state).
+ *
+ * A SEGMENT is one parameter tensor; a block of mb_adamw_step owns 4096 consecutive elements of one
+ * segment: block_prefix[i] = first block of segment i (i32 [n_segments + 1], device), n_blocks =
+ * block_prefix[n_segments] = sum of mb_optim_blocks(numel_i).  hyper[group] carries the values the host
+ * schedule assigns each step; state holds the step counter and the scalars shared by all blocks.
+ * Call order per step:
+ *   clip_norm > 0 or skip_norm > 0:  mb_sumsq (per gradient bucket, into consecutive partials) ->
+ *       mb_optim_prepare(partials) -> mb_adamw_step(partials = NULL)
+ *   otherwise:  mb_optim_prepare(n_partials = 0) -> mb_adamw_step(partials [n_blocks]) -> mb_optim_finish
+ * Either way state->grad_norm ends up holding the L2 norm of the (unclipped) gradient. */
+typedef struct mb_optim_segment {
+  float* param;     /* f32 [numel] */
+  float* grad;      /* f32 [numel] */
+  float* exp_avg;   /* f32 [numel] */
+  float* exp_avg_sq;/* f32 [numel] */
+  void* shadow;     /* bf16 [numel] or NULL: rewritten with the updated parameter */
+  int64_t numel;
+  int32_t group;    /* index into the hyper table */
+  int32_t flags;    /* bit 0: all pointers 16-byte aligned (shadow 8) -> vector path */
+} mb_optim_segment;
+
+typedef struct mb_optim_hyper {
+  float lr;           /* param_group['lr'] before lr_scale */
+  float lr_scale;     /* layer-wise lr decay factor (optim_factory.py:70-74) */
+  float weight_decay; /* param_group['weight_decay'] */
+  float pad_;
+} mb_optim_hyper;
+
+typedef struct mb_optim_state {
+  int64_t step;          /* completed optimizer steps */
+  float bias_corr1;      /* 1 - beta1^step */
+  float bias_corr2_sqrt; /* sqrt(1 - beta2^step) */
+  float clip_coef;       /* factor applied to the gradient this step (1 when not clipping) */
+  float grad_norm;       /* L2 norm of the gradient before clipping */
+  int32_t skipped;       /* 1 when the step was dropped (norm >= skip_norm) */
+  int32_t pad_;
+} mb_optim_state;
+
+int64_t mb_optim_blocks(int64_t numel);
+int mb_sumsq(const float* x, int64_t n, float* partials, int32_t n_partials, void* stream);
+int mb_optim_prepare(mb_optim_state* state, const float* partials, int32_t n_partials, float clip_norm,
+                     float skip_norm, float beta1, float beta2, void* stream);
+int mb_adamw_step(const mb_optim_segment* segments, const int32_t* block_prefix, int32_t n_segments,
+                  int64_t n_blocks, const mb_optim_hyper* hyper, const mb_optim_state* state, float beta1,
+                  float beta2, float eps, int32_t zero_grad, float* partials, void* stream);
+int mb_optim_finish(mb_optim_state* state, const float* partials, int64_t n_partials, void* stream);
+
+/* ---------------------------------------------------------------- mask sampling (8(f2)) ----- */
+/* MIRAGEModel.generate_random_masks (+ sample_alphas) in one kernel, one CTA per sample
+ * (mirage/model.py:168-239, :145-166): Dirichlet(alphas) split of n_encoded over the tasks, random subset
+ * per task, global order with the visible tokens first.  Same distribution as the reference, its own
+ * documented Philox4x32-10 stream (csrc/masks.cu) keyed by `seed` and the device-resident *draw_counter,
+ * which the kernel advances by one per call (so a CUDA-graph replay draws fresh masks).
+ * task_counts i32 [n_tasks] and alphas f32 [n_tasks] are HOST arrays (n_tasks <= 8).
+ * Outputs: task_masks i64 [B, n_all] (tasks concatenated in order; 0 = visible, 1 = masked),
+ * ids_keep i64 [B, n_encoded], ids_restore i64 [B, n_all].  done_counter: u32 device scratch, zero-initialised. */
+int mb_sample_masks(uint64_t seed, uint64_t* draw_counter, uint32_t* done_counter, const int32_t* task_counts,
+                    const float* alphas, int32_t n_tasks, int64_t batch, int64_t n_encoded,
+                    int32_t uniform_tasks, int64_t* task_masks, int64_t* ids_keep, int64_t* ids_restore,
+                    void* stream);
+
+/* ---------------------------------------------------------------- input pipeline (8(f3)) ---- */
+/* DataAugmentationForMIRAGE on the device (mutils/datasets_pretrain.py:18-83, loading :172-185): raw uint8
+ * [B, H, W] in, network inputs out.  params f32 [B, 8] = {flip, shift, m00, m01, m02, m10, m11, m12} per sample
+ * (inverse affine matrix in torchvision's centred convention, see csrc/augment.cu).
+ *   mb_augment_image : out f32 [B, 1, H, W] = affine(clip(flip(src) / 255 + shift, 0, 1)), bilinear, zero fill
+ *   mb_augment_labels: out i64 [B, OH, OW]  = nearest-resize(round(affine(flip(src)))) (bilinear on the class ids,
+ *                      as torchvision does for integer tensors) */
+int mb_augment_image(const uint8_t* src, const float* params, float* out, int64_t batch, int32_t height,
+                     int32_t width, void* stream);
+int mb_augment_labels(const uint8_t* src, const float* params, int64_t* out, int64_t batch, int32_t height,
+                      int32_t width, int32_t out_height, int32_t out_width, void* stream);
+
 /* ---------------------------------------------------------------- adapters ----------------- */
 /* SemSegInputAdapter (mirage/input_adapters.py:226-229): class-embedding lookup fused with patch
  * extraction.  out[m, c*P*Q + ph*Q + pw] = class_emb[labels[b, nh*P+ph, nw*Q+pw], c] (bf16), the A

@@ -64,6 +64,21 @@ class AttnBwdArgs(C.Structure):
     ]
 
 
+class OptimSegment(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p),
+                ("exp_avg_sq", C.c_void_p), ("shadow", C.c_void_p), ("numel", C.c_int64),
+                ("group", C.c_int32), ("flags", C.c_int32)]
+
+
+class OptimHyper(C.Structure):
+    _fields_ = [("lr", C.c_float), ("lr_scale", C.c_float), ("weight_decay", C.c_float), ("pad_", C.c_float)]
+
+
+class OptimState(C.Structure):
+    _fields_ = [("step", C.c_int64), ("bias_corr1", C.c_float), ("bias_corr2_sqrt", C.c_float),
+                ("clip_coef", C.c_float), ("grad_norm", C.c_float), ("skipped", C.c_int32), ("pad_", C.c_int32)]
+
+
 _lib = None
 
 
@@ -84,7 +99,9 @@ def _declare(lib):
     lib.mb_attn_bwd_workspace.argtypes = [i64, i64, i64, i64, i32]
     lib.mb_masked_loss_workspace.restype = C.c_int64
     lib.mb_masked_loss_workspace.argtypes = [i64, i64, i64]
-    for name in ("mb_layernorm_bwd_workspace", "mb_colsum_workspace"):
+    lib.mb_optim_blocks.restype = C.c_int64
+    lib.mb_optim_blocks.argtypes = [i64]
+    for name in ("mb_layernorm_bwd_workspace", "mb_colsum_workspace", "mb_ln_meanpool_workspace"):
         getattr(lib, name).restype = C.c_int64
         getattr(lib, name).argtypes = [i64, i64]
     # the remaining entry points are declared by signature table so the loader and the symbol
@@ -117,12 +134,23 @@ SIGNATURES: dict[str, list] = {
     "mb_masked_mse_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "mb_masked_ce_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp],
     "mb_masked_ce_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp],
+    "mb_ln_meanpool_fwd": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _f32, _vp],
+    "mb_ln_meanpool_bwd": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _i64,
+                           _i64, _vp],
+    "mb_sumsq": [_vp, _i64, _vp, _i32, _vp],
+    "mb_optim_prepare": [_vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp],
+    "mb_adamw_step": [_vp, _vp, _i32, _i64, _vp, _vp, _f32, _f32, _f32, _i32, _vp, _vp],
+    "mb_optim_finish": [_vp, _vp, _i64, _vp],
+    "mb_sample_masks": [C.c_uint64, _vp, _vp, C.POINTER(C.c_int32), C.POINTER(C.c_float), _i32, _i64, _i64, _i32,
+                        _vp, _vp, _vp, _vp],
+    "mb_augment_image": [_vp, _vp, _vp, _i64, _i32, _i32, _vp],
+    "mb_augment_labels": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
 }
 
 # every symbol include/mirage_b200.h declares
 EXPORTED = ["mb_last_error", "mb_version", "mb_sm_count", "mb_clear_tensor_map_cache", "mb_gemm",
             "mb_attn_fwd", "mb_attn_bwd", "mb_attn_bwd_workspace", "mb_layernorm_bwd_workspace",
-            "mb_colsum_workspace", "mb_masked_loss_workspace"]
+            "mb_colsum_workspace", "mb_masked_loss_workspace", "mb_ln_meanpool_workspace", "mb_optim_blocks"]
 
 
 def lib():

@@ -63,6 +63,7 @@ class GradBucketAllReduce:
             groups[-1].append(p)
             size += padded(p.numel())
         self.buckets: List[_Bucket] = []
+        self._defer = False
         self._owner = {}
         self._reported = set()
         self._offset = {}
@@ -87,12 +88,31 @@ class GradBucketAllReduce:
             Fn.set_grad_sink(self)
 
     # -- gradient sink protocol ------------------------------------------------------------------
+    def _view(self, p: torch.Tensor) -> torch.Tensor:
+        b = self._owner[p]
+        off = self._offset[p]
+        return b.flat[off:off + p.numel()].view_as(p)
+
+    def _check_attached(self, p: torch.Tensor):
+        """``p.grad`` must still be the bucket view: ``optimizer.zero_grad()`` (set_to_none=True by default)
+        or an assignment to ``p.grad`` detaches it, after which autograd would accumulate into a fresh tensor
+        while the all-reduce ships the (zero) bucket -- ranks would diverge silently."""
+        b = self._owner[p]
+        g = p.grad
+        if g is None or g.data_ptr() != b.flat.data_ptr() + 4 * self._offset[p]:
+            raise RuntimeError(
+                "GradBucketAllReduce: a parameter's .grad is no longer a view into its all-reduce bucket "
+                "(use ddp.zero_grad() instead of optimizer.zero_grad(), and never assign p.grad)")
+
     def target(self, p: torch.Tensor):
         """fp32 buffer the backward kernels accumulate p's gradient into (None: not managed here)."""
         if p not in self._owner:
             return None
-        g = p.grad
-        return g if (g is not None and g.dtype == torch.float32 and g.is_contiguous()) else None
+        self._check_attached(p)
+        if self._owner[p].work is not None:
+            raise RuntimeError("GradBucketAllReduce: backward entered while a bucket's all-reduce is still in "
+                               "flight (call ddp.finish() first, or use ddp.no_sync() to accumulate)")
+        return p.grad
 
     def done(self, p: torch.Tensor):
         self._on_grad_ready(p)
@@ -104,10 +124,14 @@ class GradBucketAllReduce:
         # does), so every parameter is counted at most once per step
         if p in self._reported:
             return
+        self._check_attached(p)
         self._reported.add(p)
         b = self._owner[p]
+        if b.work is not None:
+            raise RuntimeError("GradBucketAllReduce: a gradient arrived for a bucket whose all-reduce is in flight "
+                               "(second backward before finish(); use ddp.no_sync() for gradient accumulation)")
         b.pending -= 1
-        if b.pending == 0:
+        if b.pending == 0 and not self._defer:
             self._launch(b)
 
     def _launch(self, b: _Bucket):
@@ -115,12 +139,36 @@ class GradBucketAllReduce:
             op = dist.ReduceOp.AVG if (self.average and self._nccl) else dist.ReduceOp.SUM
             b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
 
+    # -- gradient accumulation ---------------------------------------------------------------------
+    def no_sync(self):
+        """Context manager: backward passes inside it only ACCUMULATE into the buckets (no all-reduce is
+        launched); the exchange happens in the first backward outside it / in ``finish()``.  Mirrors
+        ``DistributedDataParallel.no_sync``."""
+        ddp = self
+
+        class _NoSync:
+            def __enter__(self_):
+                self_.prev = ddp._defer
+                ddp._defer = True
+
+            def __exit__(self_, *a):
+                ddp._defer = self_.prev
+                # hooks fire once per backward: forget who reported so the next backward counts again
+                ddp._reported.clear()
+                for b in ddp.buckets:
+                    b.pending = len(b.params)
+                return False
+        return _NoSync()
+
     # -- step protocol -----------------------------------------------------------------------------
-    def zero_grad(self):
-        """Zero the buckets in place (keeps ``param.grad`` as views; never set grads to None)."""
+    def zero_grad(self, memset: bool = True):
+        """Zero the buckets in place (keeps ``param.grad`` as views; never set grads to None).
+        ``memset=False`` only resets the bookkeeping: for optimizers that zero the gradients inside their own
+        update pass (``optim.FusedAdamW(zero_grad_in_step=True)``)."""
         self._reported.clear()
         for b in self.buckets:
-            b.flat.zero_()
+            if memset:
+                b.flat.zero_()
             b.pending = len(b.params)
             b.work = None
             for p in b.params:

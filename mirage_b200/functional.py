@@ -24,28 +24,72 @@ from . import ops
 # ---------------------------------------------------------------------------------------------
 # bf16 weight shadows
 # ---------------------------------------------------------------------------------------------
-_shadow: dict[int, tuple] = {}   # id(param) -> (weakref(param), version, data_ptr, bf16 copy)
+# Every fp32 weight that feeds a tensor-core GEMM has ONE persistent bf16 twin.  The buffer's address never
+# changes for the life of the parameter, so kernels captured in a CUDA graph keep reading the right memory:
+#   * whoever modifies the parameter through PyTorch (an eager optimizer, load_state_dict, .copy_) bumps its
+#     version counter; the next bf16_weight() call re-casts INTO the same buffer;
+#   * optim.FusedAdamW rewrites parameter and twin together in its update kernel (raw pointers: the version
+#     counter does not move, the entry stays valid, no cast kernel runs at all);
+#   * graphs.GraphedCallable.capture() calls invalidate_weight_cache() first when the captured region does not
+#     update the twins itself, so the casts are recorded and every replay refreshes them.
+class _Shadow:
+    __slots__ = ("ref", "version", "ptr", "buf")
+
+    def __init__(self, ref, version, ptr, buf):
+        self.ref, self.version, self.ptr, self.buf = ref, version, ptr, buf
+
+
+_shadow: dict[int, _Shadow] = {}   # id(param) -> entry
+_shadow_epoch = [0]                # bumped whenever a twin is created or dropped (optimizer tables key on it)
 
 
 def bf16_weight(p: torch.Tensor) -> torch.Tensor:
-    """bf16 copy of an fp32 weight, cached until the parameter is modified in place or replaced.
-    The entry is tied to the parameter OBJECT (weak reference): ids and allocator blocks are recycled
-    once a model is freed, so (id, version, data_ptr) alone can match a different, differently shaped
-    parameter of a later model."""
+    """bf16 twin of an fp32 weight (see above).  The entry is tied to the parameter OBJECT (weak reference):
+    ids and allocator blocks are recycled once a model is freed, so (id, data_ptr) alone can match a
+    different, differently shaped parameter of a later model."""
     if p.dtype == torch.bfloat16:
         return p
     key = id(p)
-    ver = p._version
     ent = _shadow.get(key)
-    if ent is not None and ent[0]() is p and ent[1] == ver and ent[2] == p.data_ptr():
-        return ent[3]
+    if ent is not None and ent.ref() is p and ent.ptr == p.data_ptr() and ent.buf.shape == p.shape:
+        if ent.version != p._version:
+            ops.cast_bf16(p.detach().contiguous(), out=ent.buf)
+            ent.version = p._version
+        return ent.buf
     w = ops.cast_bf16(p.detach().contiguous())
-    _shadow[key] = (weakref.ref(p, lambda _r, k=key: _shadow.pop(k, None)), ver, p.data_ptr(), w)
+
+    def _drop(_r, k=key):
+        if _shadow.pop(k, None) is not None:
+            _shadow_epoch[0] += 1
+    _shadow[key] = _Shadow(weakref.ref(p, _drop), p._version, p.data_ptr(), w)
+    _shadow_epoch[0] += 1
     return w
+
+
+def shadow_of(p: torch.Tensor) -> Optional[torch.Tensor]:
+    """The persistent bf16 twin of ``p`` if one exists and is current (used by optim.FusedAdamW)."""
+    ent = _shadow.get(id(p))
+    if ent is None or ent.ref() is not p or ent.ptr != p.data_ptr():
+        return None
+    if ent.version != p._version:
+        ops.cast_bf16(p.detach().contiguous(), out=ent.buf)
+        ent.version = p._version
+    return ent.buf
+
+
+def shadow_epoch() -> int:
+    return _shadow_epoch[0]
+
+
+def invalidate_weight_cache():
+    """Mark every twin stale: the next use re-casts in place (same address)."""
+    for ent in _shadow.values():
+        ent.version = -1
 
 
 def clear_weight_cache():
     _shadow.clear()
+    _shadow_epoch[0] += 1
 
 
 def grad_needed(*tensors) -> bool:
@@ -77,9 +121,18 @@ def _as_bf16(t: torch.Tensor) -> torch.Tensor:
     return ops.cast_bf16(t.contiguous())
 
 
+_SMS = [0]
+
+
+def _sm_count() -> int:
+    if _SMS[0] == 0:
+        _SMS[0] = int(L.lib().mb_sm_count())
+    return _SMS[0]
+
+
 def _wgrad_splits(n_out: int, k_in: int, tokens: int) -> int:
     tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
-    sms = 148
+    sms = _sm_count()
     kblocks = (tokens + 63) // 64
     s = max(1, min(sms // max(tiles, 1), kblocks // 4))
     return max(1, s)
@@ -358,6 +411,10 @@ class _Block(Function):
         dyb = _as_bf16(dx2)
         ps = (n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
         tg = [_sink_of(q) for q in ps]
+        for wi, bi in ((0, 1), (6, 7)):
+            # the LayerNorm-backward kernel accumulates both parameter gradients or neither
+            if tg[wi] is None or tg[bi] is None:
+                tg[wi] = tg[bi] = None
         # MLP branch
         d_fc2_w = wgrad(dyb, g, into=tg[10])
         d_fc2_b = ops.colsum(dyb, into=tg[11])
@@ -620,20 +677,68 @@ def masked_ce(logits, target, mask, scale, smoothing=0.0):
     return _MaskedCE.apply(logits, target, mask, scale, smoothing)
 
 
-# one-entry cache: the three output adapters all project the same encoder tokens (K12 in SURVEY.md)
+# ---------------------------------------------------------------------------------------------
+# LayerNorm + token mean-pool (classification tail, mirage_wrapper.py:217-244)
+# ---------------------------------------------------------------------------------------------
+class _LnMeanPool(Function):
+    """x fp32 [B, N, D] -> fp32 [B, len(ranges) * D]: for every (begin, end) row range the mean over those
+    tokens of LayerNorm(x), concatenated.  The normalised [B, N, D] tensor is never materialised."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, ranges, need):
+        x = x.contiguous()
+        B, N, D = x.shape
+        pooled = torch.empty((B, len(ranges) * D), dtype=torch.float32, device=x.device)
+        saved = []
+        for i, (r0, r1) in enumerate(ranges):
+            _, xm, mean, rstd = ops.ln_meanpool_fwd(x, gamma, beta, eps, r0, r1, pooled=pooled, col_offset=i * D)
+            saved += [xm, mean, rstd]
+        if need:
+            ctx.save_for_backward(x, gamma, beta, *saved)
+            ctx.ranges = ranges
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dp):
+        x, gamma, beta, *saved = ctx.saved_tensors
+        D = x.shape[2]
+        dp = dp.contiguous().float()
+        tg_w, tg_b = _sink_of(gamma), _sink_of(beta)
+        acc = tg_w is not None and tg_b is not None
+        dx = dg = db = None
+        for i, (r0, r1) in enumerate(ctx.ranges):
+            xm, mean, rstd = saved[3 * i: 3 * i + 3]
+            dx, dg, db = ops.ln_meanpool_bwd(dp, i * D, x, gamma, mean, rstd, xm, r0, r1, dx=dx,
+                                             d_gamma=tg_w if acc else dg, d_beta=tg_b if acc else db,
+                                             accumulate=acc or i > 0)
+        if acc:
+            _grad_sink.done(gamma)
+            _grad_sink.done(beta)
+            dg = db = None
+        return dx, dg, db, None, None, None
+
+
+def ln_meanpool(x, gamma, beta, eps, ranges):
+    return _LnMeanPool.apply(x, gamma, beta, eps, tuple(ranges), grad_needed(x, gamma, beta))
+
+
+# one-entry cache: the three output adapters all project the same encoder tokens (K12 in SURVEY.md).
+# The source tensor is held STRONGLY until the next different tensor replaces it (callers pass a temporary
+# reshape view that would otherwise die at once and never hit).
 _last_cast: dict = {}
 
 
 def cached_bf16(x: torch.Tensor) -> torch.Tensor:
-    key = (x.data_ptr(), x._version, tuple(x.shape), x.requires_grad, torch.is_grad_enabled())
-    if _last_cast.get('key') == key and _last_cast.get('src') is not None and _last_cast['src']() is not None:
+    key = (x.data_ptr(), x._version, tuple(x.shape), tuple(x.stride()), x.requires_grad, torch.is_grad_enabled())
+    # 'src' is alive, so a matching (pointer, version, geometry) cannot be recycled storage: same data
+    if _last_cast.get('key') == key and _last_cast.get('src') is not None:
         return _last_cast['out']
-    import weakref
     out = to_bf16(x)
     _last_cast['key'] = key
-    try:
-        _last_cast['src'] = weakref.ref(x)
-    except TypeError:
-        _last_cast['src'] = None
+    _last_cast['src'] = x
     _last_cast['out'] = out
     return out
+
+
+def drop_cast_cache():
+    _last_cast.clear()

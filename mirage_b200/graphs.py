@@ -10,6 +10,15 @@ nothing itself and never synchronises, so a whole step can be captured once and 
 
 Anything that must stay on the host (the reference samples the Dirichlet token split on the CPU,
 mirage/model.py:205-207) runs before the replay and writes into the fixed input tensors.
+
+Weights: the GEMMs read persistent bf16 twins of the fp32 parameters (functional.bf16_weight).  Their
+addresses never change, but their CONTENTS only follow the parameters if something refreshes them:
+  * ``refresh_weights=True`` (default whenever autograd is enabled at capture time): every twin is marked
+    stale before capture, so the fp32 -> bf16 casts are recorded and each replay re-reads the parameters --
+    correct with an optimizer stepped eagerly outside the graph and after ``load_state_dict``;
+  * ``refresh_weights=False``: no cast is recorded (inference with frozen weights, or a captured step whose
+    optimizer -- optim.FusedAdamW -- rewrites the twins itself).  After replacing weights call ``capture()``
+    again, or ``functional.bf16_weight`` on them eagerly (it re-casts into the same buffers).
 """
 from __future__ import annotations
 
@@ -17,13 +26,16 @@ import torch
 
 
 class GraphedCallable:
-    def __init__(self, fn, warmup: int = 2):
+    def __init__(self, fn, warmup: int = 2, refresh_weights=None):
         self.fn = fn
         self.warmup = warmup
+        self.refresh_weights = refresh_weights
         self.graph = None
         self.out = None
 
     def capture(self):
+        from . import functional as Fn
+        refresh = torch.is_grad_enabled() if self.refresh_weights is None else self.refresh_weights
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -32,6 +44,8 @@ class GraphedCallable:
                 self.fn()
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        if refresh:
+            Fn.invalidate_weight_cache()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.out = self.fn()

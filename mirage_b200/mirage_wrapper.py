@@ -146,14 +146,31 @@ class MIRAGEClsGlobal(MIRAGEWrapper):
         x_d = {self.args.in_domains[0]: x}
         out, _masks = self.model(x_d, mask_inputs=False)
         B, N, D = out.shape
-        out = Fn.layer_norm(out.reshape(B * N, D), self.norm.weight, self.norm.bias, self.norm.eps,
-                            out_f32=True).reshape(B, N, D)
-        out = self.pool(out)
+        ranges = self._pool_ranges(N)
+        if ranges is not None and out.is_cuda and D % 128 == 0 and D <= 1024:
+            # fused LayerNorm + token mean (csrc/pool.cu): one pass over the encoder output
+            out = Fn.ln_meanpool(out, self.norm.weight, self.norm.bias, self.norm.eps, ranges)
+        else:
+            # a user-overridden pool(): normalise, then call it (mirage_wrapper.py:219-221)
+            out = Fn.layer_norm(out.reshape(B * N, D), self.norm.weight, self.norm.bias, self.norm.eps,
+                                out_f32=True).reshape(B, N, D)
+            out = self.pool(out)
         # [B, D] x [C, D]^T: a few MFLOP, left to the PyTorch library
         return self.head(out)
 
     def pool(self, x):
         return x[:, :-self.args.num_global_tokens, :].mean(dim=1)
+
+    _POOL_KIND = 'global'
+
+    def _pool_ranges(self, N):
+        """Token row ranges whose LayerNorm-ed mean makes up the pooled feature, or None when ``pool`` has been
+        overridden outside this module."""
+        g = self.args.num_global_tokens
+        known = {'global': MIRAGEClsGlobal.pool, 'cls': MIRAGEClsCLS.pool, 'token_mix': MIRAGEClsTokenMix.pool}
+        if type(self).pool is not known.get(self._POOL_KIND):
+            return None
+        return {'global': [(0, N - g)], 'cls': [(N - g, N)], 'token_mix': [(0, N - g), (N - g, N)]}[self._POOL_KIND]
 
     def get_output_adapters(self):
         return None
@@ -161,12 +178,16 @@ class MIRAGEClsGlobal(MIRAGEWrapper):
 
 @add_miragecls('cls')
 class MIRAGEClsCLS(MIRAGEClsGlobal):
+    _POOL_KIND = 'cls'
+
     def pool(self, x):
         return x[:, -self.args.num_global_tokens:, :].mean(dim=1)
 
 
 @add_miragecls('token_mix')
 class MIRAGEClsTokenMix(MIRAGEClsGlobal):
+    _POOL_KIND = 'token_mix'
+
     def build_head(self, factor=2):
         super().build_head(factor)
 

@@ -65,6 +65,10 @@ class MIRAGEModel(nn.Module):
         self._reference_init()
         self.input_info = None
         self.token_dist = None
+        # 'reference': the reference's torch op sequence (bit-exact masks given the same generators);
+        # 'device': one fused sampling kernel (same distribution, own random stream; see set_mask_sampler)
+        self.mask_sampler = 'reference'
+        self._mask_rng = None
 
     # -- initialisation: same distributions as mirage/model.py:95-121 -----------------------------
     def _reference_init(self):
@@ -124,6 +128,8 @@ class MIRAGEModel(nn.Module):
         first = next(iter(input_tokens.values()))
         B, device = first.shape[0], first.device
         counts = [t.shape[1] for t in input_tokens.values()]
+        if self.mask_sampler == 'device' and first.is_cuda:
+            return self._device_masks(input_tokens, num_encoded_tokens, alphas, sample_tasks_uniformly)
 
         if self.token_dist is None:
             total = sum(counts)
@@ -155,6 +161,45 @@ class MIRAGEModel(nn.Module):
         mask_all = torch.ones_like(mask_all)
         mask_all[:, :num_encoded_tokens] = 0
         mask_all = torch.gather(mask_all, dim=1, index=ids_restore)
+        task_masks = dict(zip(input_tokens.keys(), torch.split(mask_all, counts, dim=1)))
+        return task_masks, ids_keep, ids_restore
+
+    # -- on-device sampler ------------------------------------------------------------
+    def set_mask_sampler(self, kind: str = 'device', seed: Optional[int] = None):
+        """``'device'``: ``generate_random_masks`` becomes ONE kernel launch (csrc/masks.cu) -- Dirichlet split,
+        per-task random subsets and the global visible-first order computed on the GPU from a Philox stream
+        keyed by ``seed`` (default: drawn once from torch's CPU generator) and a device-resident draw counter
+        the kernel advances itself, so the call is CUDA-graph capturable and every replay draws fresh masks.
+        Same distribution as the reference sampler (tests/test_gpu_masks.py), different random numbers.
+        ``'reference'`` restores the bit-exact reference path."""
+        if kind not in ('reference', 'device'):
+            raise ValueError(f'unknown mask sampler {kind!r}')
+        self.mask_sampler = kind
+        if kind == 'device':
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            dev = self.global_tokens.device
+            self._mask_rng = {'seed': int(seed), 'draw': torch.zeros(1, dtype=torch.int64, device=dev),
+                              'done': torch.zeros(1, dtype=torch.int32, device=dev)}
+        return self
+
+    def _device_masks(self, input_tokens: Dict[str, Tensor], num_encoded_tokens: int, alphas,
+                      sample_tasks_uniformly: bool):
+        first = next(iter(input_tokens.values()))
+        B = first.shape[0]
+        counts = [t.shape[1] for t in input_tokens.values()]
+        rng = self._mask_rng
+        if rng is None or rng['draw'].device != first.device:
+            self.set_mask_sampler('device', seed=None if rng is None else rng['seed'])
+            rng = self._mask_rng
+            if rng['draw'].device != first.device:
+                rng['draw'] = rng['draw'].to(first.device)
+                rng['done'] = rng['done'].to(first.device)
+        if isinstance(alphas, Tensor):
+            alphas = alphas.flatten().tolist()
+        al = [float(alphas)] * len(counts) if isinstance(alphas, (int, float)) else [float(a) for a in alphas]
+        mask_all, ids_keep, ids_restore = ops.sample_masks(rng['seed'], rng['draw'], rng['done'], counts, al, B,
+                                                           num_encoded_tokens, sample_tasks_uniformly)
         task_masks = dict(zip(input_tokens.keys(), torch.split(mask_all, counts, dim=1)))
         return task_masks, ids_keep, ids_restore
 

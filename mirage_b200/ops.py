@@ -267,10 +267,14 @@ def fill_global_rows(global_tokens: torch.Tensor, out: torch.Tensor, row_offset:
     return out
 
 
-def cast_bf16(x: torch.Tensor) -> torch.Tensor:
-    _req_cuda(x)
+def cast_bf16(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 -> bf16; ``out``: an existing contiguous bf16 tensor of the same shape, rewritten in place."""
+    _req_cuda(x, out)
     assert x.dtype == torch.float32 and x.is_contiguous()
-    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    else:
+        assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.numel() == x.numel()
     with _rec("cast_bf16", 6.0 * x.numel(), "byte"):
         L.check(L.lib().mb_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()),
                 "mb_cast_f32_to_bf16")
@@ -410,3 +414,111 @@ def masked_ce_bwd(logits, target, mask, coef, gout, scale: int, smoothing: float
                                          gout.data_ptr(), dl.data_ptr(), B, Cc, H, W, scale, smoothing,
                                          _stream()), "mb_masked_ce_bwd")
     return dl
+
+
+# ---------------------------------------------------------------------------------------------
+# LayerNorm + token mean-pool (classification tail)
+# ---------------------------------------------------------------------------------------------
+def ln_meanpool_fwd(x: torch.Tensor, gamma, beta, eps: float, row_begin: int, row_end: int,
+                    pooled: torch.Tensor | None = None, col_offset: int = 0):
+    """x f32 [B, N, D] -> pooled f32 [B, D] = mean over rows [row_begin, row_end) of LayerNorm(x).
+    ``pooled`` / ``col_offset``: write into columns [col_offset, col_offset + D) of a wider [B, k*D] buffer.
+    Returns (pooled, xhat_mean, mean, rstd)."""
+    _req_cuda(x, gamma, beta, pooled)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+    B, N, D = x.shape
+    if pooled is None:
+        pooled = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    assert pooled.dtype == torch.float32 and pooled.stride(1) == 1
+    xhat_mean = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    mean = torch.empty((B, N), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((B, N), dtype=torch.float32, device=x.device)
+    ws = torch.empty(L.lib().mb_ln_meanpool_workspace(B, D), dtype=torch.uint8, device=x.device)
+    with _rec("ln_meanpool_fwd", 4.0 * B * (row_end - row_begin) * D, "byte", kernels=2):
+        L.check(L.lib().mb_ln_meanpool_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                           pooled.data_ptr() + 4 * col_offset, pooled.stride(0),
+                                           xhat_mean.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(),
+                                           B, N, D, row_begin, row_end, eps, _stream()), "mb_ln_meanpool_fwd")
+    return pooled, xhat_mean, mean, rstd
+
+
+def ln_meanpool_bwd(d_pooled: torch.Tensor, col_offset: int, x, gamma, mean, rstd, xhat_mean, row_begin: int,
+                    row_end: int, dx: torch.Tensor | None = None, d_gamma=None, d_beta=None,
+                    accumulate: bool = False):
+    """Returns (dx f32 [B, N, D], d_gamma, d_beta).  With ``dx`` given, only the pooled rows are written
+    (second range of the token_mix pooling); ``accumulate`` adds into d_gamma / d_beta."""
+    _req_cuda(d_pooled, x, gamma, mean, rstd, xhat_mean, dx)
+    B, N, D = x.shape
+    assert d_pooled.dtype == torch.float32 and d_pooled.stride(1) == 1
+    zero_outside = dx is None
+    if dx is None:
+        dx = torch.empty_like(x)
+    if d_gamma is None:
+        assert not accumulate
+        d_gamma = torch.empty(D, dtype=torch.float32, device=x.device)
+        d_beta = torch.empty(D, dtype=torch.float32, device=x.device)
+    with _rec("ln_meanpool_bwd", 8.0 * B * (row_end - row_begin) * D + (4.0 * B * N * D if zero_outside else 0.0),
+              "byte", kernels=2):
+        L.check(L.lib().mb_ln_meanpool_bwd(d_pooled.data_ptr() + 4 * col_offset, d_pooled.stride(0), x.data_ptr(),
+                                           gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), xhat_mean.data_ptr(),
+                                           dx.data_ptr(), d_gamma.data_ptr(), d_beta.data_ptr(),
+                                           1 if accumulate else 0, 1 if zero_outside else 0, B, N, D, row_begin,
+                                           row_end, _stream()), "mb_ln_meanpool_bwd")
+    return dx, d_gamma, d_beta
+
+
+# ---------------------------------------------------------------------------------------------
+# on-device mask sampling (SURVEY.md 8(f2))
+# ---------------------------------------------------------------------------------------------
+def sample_masks(seed: int, draw_counter: torch.Tensor, done_counter: torch.Tensor, counts, alphas,
+                 batch: int, n_encoded: int, uniform_tasks: bool = False):
+    """Returns (mask_all i64 [B, n_all], ids_keep i64 [B, n_encoded], ids_restore i64 [B, n_all]).
+    ``draw_counter``: 1-element int64 CUDA tensor (advanced by the kernel); ``done_counter``: 1-element
+    int32 CUDA tensor, zero-initialised scratch."""
+    _req_cuda(draw_counter, done_counter)
+    assert draw_counter.dtype == torch.int64 and done_counter.dtype == torch.int32
+    dev = draw_counter.device
+    n_all = int(sum(counts))
+    mask_all = torch.empty((batch, n_all), dtype=torch.int64, device=dev)
+    keep = torch.empty((batch, n_encoded), dtype=torch.int64, device=dev)
+    restore = torch.empty((batch, n_all), dtype=torch.int64, device=dev)
+    c_counts = (C.c_int32 * len(counts))(*[int(c) for c in counts])
+    c_alphas = (C.c_float * len(counts))(*[float(a) for a in alphas])
+    with _rec("sample_masks", 8.0 * batch * (2 * n_all + n_encoded), "byte"):
+        L.check(L.lib().mb_sample_masks(int(seed) & 0xFFFFFFFFFFFFFFFF, draw_counter.data_ptr(),
+                                        done_counter.data_ptr(), c_counts, c_alphas, len(counts), batch, n_encoded,
+                                        1 if uniform_tasks else 0, mask_all.data_ptr(), keep.data_ptr(),
+                                        restore.data_ptr(), _stream()), "mb_sample_masks")
+    return mask_all, keep, restore
+
+
+# ---------------------------------------------------------------------------------------------
+# device-side input pipeline (SURVEY.md 8(f3))
+# ---------------------------------------------------------------------------------------------
+def augment_image(src_u8: torch.Tensor, params: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """uint8 [B, H, W] + params f32 [B, 8] -> f32 [B, 1, H, W] (flip, intensity shift, affine warp)."""
+    _req_cuda(src_u8, params, out)
+    assert src_u8.dtype == torch.uint8 and src_u8.is_contiguous() and src_u8.dim() == 3
+    assert params.dtype == torch.float32 and params.is_contiguous() and params.shape == (src_u8.shape[0], 8)
+    B, H, W = src_u8.shape
+    if out is None:
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=src_u8.device)
+    with _rec("augment_image", 5.0 * B * H * W, "byte"):
+        L.check(L.lib().mb_augment_image(src_u8.data_ptr(), params.data_ptr(), out.data_ptr(), B, H, W, _stream()),
+                "mb_augment_image")
+    return out
+
+
+def augment_labels(src_u8: torch.Tensor, params: torch.Tensor, out_hw, out: torch.Tensor | None = None):
+    """uint8 class map [B, H, W] + params f32 [B, 8] -> int64 [B, OH, OW]."""
+    _req_cuda(src_u8, params, out)
+    assert src_u8.dtype == torch.uint8 and src_u8.is_contiguous() and src_u8.dim() == 3
+    assert params.dtype == torch.float32 and params.is_contiguous() and params.shape == (src_u8.shape[0], 8)
+    B, H, W = src_u8.shape
+    OH, OW = out_hw
+    if out is None:
+        out = torch.empty((B, OH, OW), dtype=torch.int64, device=src_u8.device)
+    with _rec("augment_labels", 1.0 * B * H * W / max(1, (H // OH) * (W // OW)) * 4 + 8.0 * B * OH * OW, "byte"):
+        L.check(L.lib().mb_augment_labels(src_u8.data_ptr(), params.data_ptr(), out.data_ptr(), B, H, W, OH, OW,
+                                          _stream()), "mb_augment_labels")
+    return out

@@ -10,9 +10,10 @@ plus whole-tensor checksums.
 Fixtures
   encoder_{base,large}.pt  hf/mirage_hf.py MIRAGEWrapper forward, bscan+slo 512x512, B=1
   masks.pt                 MIRAGEModel.generate_random_masks under fixed seeds (bit-exact target)
-  pretrain_{tiny,base}.pt  MIRAGEModel (+3 SpatialOutputAdapters) forward, masked losses, gradients
+  pretrain_{tiny,base,large}.pt  MIRAGEModel (+3 SpatialOutputAdapters) forward, masked losses, gradients
   criterion.pt             MaskedMSELoss / MaskedCrossEntropyLoss incl. empty- and partial-mask cases
-  cls.pt                   miragecls_factory['global'|'cls'|'token_mix'] logits + grads (tiny encoder)
+  cls.pt                   miragecls_factory['global'|'cls'|'token_mix'] logits + grads (ViT-B encoder)
+  cls_large.pt             miragecls_factory['global'] logits + grads, ViT-L encoder (BASELINE configs[4])
 """
 from __future__ import annotations
 
@@ -207,15 +208,16 @@ def gen_criterion(ref_crit):
     print("criterion", out["mse"], out["ce"])
 
 
-def gen_cls(ref_wrap, ref_model, ref_in):
-    """Classification heads on a small encoder (dim 128, depth 2): the wrapper classes need a
-    checkpoint file, so one is synthesised in /tmp with the recipe of SURVEY.md 8(c)."""
+def gen_cls(ref_wrap, ref_model, ref_in, size="base", pools=("global", "cls", "token_mix"), fname="cls.pt"):
+    """Classification heads on the ViT-B (cls.pt) / ViT-L (cls_large.pt, BASELINE configs[4]) encoder:
+    the wrapper classes need a checkpoint file, so one is synthesised in /tmp with the recipe of
+    SURVEY.md 8(c)."""
     import tempfile
-    args = argparse.Namespace(model="miragepre_base", out_domains=[], decoder_dim=256, decoder_depth=2,
+    args = argparse.Namespace(model=f"miragepre_{size}", out_domains=[], decoder_dim=256, decoder_depth=2,
                               decoder_num_heads=8, decoder_use_task_queries=True, decoder_use_xattn=True,
                               num_global_tokens=1, drop_path=0.0, grid_sizes={"bscan": [16, 16]})
     out = {}
-    for pool in ("global", "cls", "token_mix"):
+    for pool in pools:
         cls_t = ref_wrap.miragecls_factory[pool]
         with _quiet():
             helper = cls_t.__new__(cls_t)
@@ -244,12 +246,12 @@ def gen_cls(ref_wrap, ref_model, ref_in):
                      "grad_norm": {k: p.grad.norm().item() for k, p in m.named_parameters() if p.grad is not None},
                      "head_grad": m.head.weight.grad.clone(), "n_params": sum(p.numel() for p in m.parameters())}
         print("cls", pool, logits.detach().flatten()[:3].tolist(), loss.item())
-    torch.save({"weights_seed": 21, "input_seed": 9, "mask_seed": 13, "size": "base", "out": out}, GOLDEN / "cls.pt")
+    torch.save({"weights_seed": 21, "input_seed": 9, "mask_seed": 13, "size": size, "out": out}, GOLDEN / fname)
 
 
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    which = set(sys.argv[1:]) or {"encoder", "masks", "pretrain", "criterion", "cls"}
+    which = set(sys.argv[1:]) or {"encoder", "masks", "pretrain", "pretrain_large", "criterion", "cls", "cls_large"}
     ref_hf, ref_model, ref_in, ref_out, ref_crit, ref_wrap = import_reference()
     torch.set_num_threads(8)
     if "encoder" in which:
@@ -262,5 +264,9 @@ if __name__ == "__main__":
     if "pretrain" in which:
         gen_pretrain(ref_model, ref_in, ref_out, ref_crit, "tiny", 128, 2, 2, 3, 64)
         gen_pretrain(ref_model, ref_in, ref_out, ref_crit, "base", 768, 12, 12, 2, 1024)
+    if "pretrain_large" in which:   # BASELINE configs[3] at its real model size (ViT-L), batch 2
+        gen_pretrain(ref_model, ref_in, ref_out, ref_crit, "large", 1024, 24, 16, 2, 8192)
     if "cls" in which:
         gen_cls(ref_wrap, ref_model, ref_in)
+    if "cls_large" in which:        # BASELINE configs[4] at its real model size (ViT-L), batch 2
+        gen_cls(ref_wrap, ref_model, ref_in, size="large", pools=("global",), fname="cls_large.pt")

@@ -40,11 +40,11 @@ def build_cls_model(pool: str, weights_seed: int, device="cpu", num_classes=5, s
     return m.to(device), sd
 
 
-def oracle_cls_logits(x: torch.Tensor, sd: dict, pool: str):
+def oracle_cls_logits(x: torch.Tensor, sd: dict, pool: str, size: str = "base"):
     """fp32 CPU oracle: patch embed -> (+ global token last) -> 12 blocks -> LayerNorm -> pool -> head.
     The reference feeds the encoder a random permutation of the 256 patch tokens; every
     pooling variant is invariant to it, so the oracle keeps the natural order."""
     from oracle import mirage_oracle as O
     msd = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
-    tok = O.light_forward({"bscan": x}, msd, 12, 12)
+    tok = O.light_forward({"bscan": x}, msd, *((12, 12) if size == "base" else (24, 16)))
     return O.cls_head(tok, sd, pool)

@@ -22,10 +22,10 @@ def _free_port():
     return p
 
 
-def _setup(batch):
+def _setup(batch, dev=None):
     from helpers import load_synth, synth_images
     from pretrain_case import MODS, build_criteria, build_pretrain_model, sample_masks
-    dev = torch.device("cuda:0")
+    dev = dev or torch.device("cuda:0")
     model, _ = build_pretrain_model("tiny")
     load_synth(model, seed=3)
     model = model.to(dev).train()
@@ -43,7 +43,7 @@ def _run(model, crits, x, masks, mods, sl):
     sum(crits[d](preds[d].float(), xs[d], mask=m[d]) for d in mods).backward()
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, backend="gloo"):
     import sys
     from pathlib import Path
     root = Path(__file__).resolve().parent.parent
@@ -51,10 +51,15 @@ def _worker(rank, world, port, ret):
         if q not in sys.path:
             sys.path.insert(0, q)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = torch.device("cuda", rank if backend == "nccl" else 0)
+    torch.cuda.set_device(dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     from mirage_b200 import functional as Fn
     from mirage_b200.ddp import GradBucketAllReduce
-    model, crits, x, masks, mods = _setup(4)
+    model, crits, x, masks, mods = _setup(4, dev)
     ddp = GradBucketAllReduce(model, bucket_mb=0.5)
     assert Fn._grad_sink is ddp and len(ddp.buckets) > 3
     for _ in range(2):
@@ -69,11 +74,11 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_two_rank_step_matches_single_process():
+def _check_two_rank(backend):
     port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, ret, backend), nprocs=2, join=True)
     got = ret["grads"]
     # single process, no sink: per-rank losses are means over 2 samples each, so the rank average equals
     # the mean of the two half-batch gradients
@@ -89,3 +94,14 @@ def test_two_rank_step_matches_single_process():
     for n, v in ref.items():
         tol = 2e-3 * v.abs().max().item() + 1e-6 * big
         assert (got[n] - v).abs().max().item() <= tol, (n, (got[n] - v).abs().max().item(), tol)
+
+
+def test_two_rank_step_matches_single_process():
+    _check_two_rank("gloo")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="the NCCL gradient path needs two GPUs")
+def test_two_gpu_nccl_step_matches_single_process():
+    """The real exchange: one process per GPU, ncclAvg all-reduce of the flat fp32 buckets launched from
+    inside backward (ddp.py _launch); averaged gradients == single-process gradients."""
+    _check_two_rank("nccl")

@@ -62,19 +62,21 @@ def test_encoder_full_batch_properties():
     assert_parity(big[:8], small, "batch 256 vs batch 8", max_rel=1e-2, cos=0.9999)
 
 
-@pytest.mark.parametrize("size,batch", [("tiny", 3), ("base", 2)])
+@pytest.mark.parametrize("size,batch", [("tiny", 3), ("base", 2), ("large", 2)])
 def test_pretrain_forward_backward_vs_oracle(size, batch):
     from pretrain_case import run_pretrain_parity
     out = run_pretrain_parity(torch.device("cuda:0"), size, batch)
     assert out["grad_min_cos"] >= 0.999
 
 
-def test_pretrain_vs_reference_golden():
-    """Losses and gradient norms against the values recorded from the reference itself."""
+@pytest.mark.parametrize("size", ["base", "large"])
+def test_pretrain_vs_reference_golden(size):
+    """Losses and gradient norms against the values recorded from the reference itself (ViT-B and the
+    ViT-L of BASELINE configs[3])."""
     from pretrain_case import MODS, b200_step, build_criteria, build_pretrain_model
     dev = torch.device("cuda:0")
-    g = torch.load(GOLDEN / "pretrain_base.pt")
-    model, _ = build_pretrain_model("base")
+    g = torch.load(GOLDEN / f"pretrain_{size}.pt")
+    model, _ = build_pretrain_model(size)
     load_synth(model, seed=g["weights_seed"])
     model = model.to(dev).train()
     x = {k: v.to(dev) for k, v in synth_images(g["batch"], MODS, seed=g["input_seed"]).items()}
@@ -158,15 +160,17 @@ def test_encode_host_pipeline_matches_forward():
         assert_parity(out, ref, f"encode_host chunk={chunk}", max_rel=1e-5, cos=0.99999)
 
 
-@pytest.mark.parametrize("pool", ["global", "cls", "token_mix"])
-def test_cls_finetune_step_vs_reference_golden(pool):
-    """BASELINE configs[4] path at test size: miragecls_factory[pool] forward + CE + backward on cuda:0
-    against logits, loss and gradient norms recorded from the reference (tests/golden/cls.pt)."""
+@pytest.mark.parametrize("pool,size", [("global", "base"), ("cls", "base"), ("token_mix", "base"),
+                                       ("global", "large")])
+def test_cls_finetune_step_vs_reference_golden(pool, size):
+    """BASELINE configs[4] path: miragecls_factory[pool] forward + CE + backward on cuda:0 against logits,
+    loss and gradient norms recorded from the reference (tests/golden/cls.pt: ViT-B, three pools;
+    cls_large.pt: the ViT-L of configs[4])."""
     from cls_case import build_cls_model
     dev = torch.device("cuda:0")
-    g = torch.load(GOLDEN / "cls.pt")
+    g = torch.load(GOLDEN / ("cls.pt" if size == "base" else "cls_large.pt"))
     ref = g["out"][pool]
-    m, _ = build_cls_model(pool, g["weights_seed"], device=dev)
+    m, _ = build_cls_model(pool, g["weights_seed"], device=dev, size=size)
     m.train()
     x = synth_images(2, ["bscan"], seed=g["input_seed"])["bscan"].to(dev)
     torch.manual_seed(g["mask_seed"])

@@ -109,6 +109,25 @@ def test_pretrain_base_golden():
     _pretrain_golden("base")
 
 
+def test_pretrain_large_golden():
+    """BASELINE configs[3] at its real model size (ViT-L + three decoders, batch 2)."""
+    _pretrain_golden("large")
+
+
+def test_cls_large_golden():
+    """BASELINE configs[4] at its real model size: miragecls_factory['global'] on the ViT-L encoder."""
+    from cls_case import build_cls_model, oracle_cls_logits
+    g = torch.load(GOLDEN / "cls_large.pt")
+    assert g["size"] == "large"
+    x = synth_images(2, ["bscan"], seed=g["input_seed"])["bscan"]
+    m, sd = build_cls_model("global", g["weights_seed"], size="large")
+    assert sum(p.numel() for p in m.parameters()) == g["out"]["global"]["n_params"]
+    with torch.no_grad():
+        logits = oracle_cls_logits(x, sd, "global", size="large")
+    ref = g["out"]["global"]["logits"]
+    assert torch.allclose(logits, ref, rtol=2e-3, atol=2e-3), (logits - ref).abs().max()
+
+
 def test_cls_heads_golden():
     """Oracle of the classification tail (mirage_wrapper.py:187-244) against logits recorded from the
     reference's miragecls_factory classes (ViT-B encoder, B=2)."""
