@@ -118,10 +118,8 @@ def cpu_oracle_throughput(workload: str, budget_s: float = 20.0, batch: int = 2,
     torch.set_num_threads(cores)
     depth, heads = (12, 12) if size == "base" else (24, 16)
     if kind == "encoder":
-        from mirage_b200.mirage_hf import MIRAGEWrapper
-        with torch.device("cpu"):
-            m = MIRAGEWrapper(size=size, modalities="-".join(mods))
-        sd = m.model.state_dict()
+        # shapes from the oracle itself: the CPU arm never imports the product package
+        sd = O.light_state_dict_shapes(mods, size)
         sd.update(synth_state_dict({k: v.shape for k, v in sd.items()}, seed))
         x = synth_images(batch, mods, seed=1234)
 
@@ -209,27 +207,55 @@ class KernelTimer:
         return agg
 
 
-def run_gpu(args):
-    import torch.distributed as dist
-    from mirage_b200 import ops
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the MIRAGE hot path has no CPU fallback "
-                         "(use --impl reference for the CPU oracle)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+def _sync_all(world):
+    torch.cuda.synchronize()
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
 
-    size, mods, per_gpu, kind = WORKLOADS[args.workload]
-    if args.batch:
-        per_gpu = args.batch
+
+def _timed(step, K, world, dev):
+    """K steps bracketed by barrier + synchronize on both sides, CUDA events, max over ranks (ms total)."""
+    import torch.distributed as dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _sync_all(world)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    _sync_all(world)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def _traffic_entry(workload, kernel):
+    """DRAM bytes per launch of `kernel` in `workload` from the committed ncu --set full captures."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            tr = json.loads((ROOT / "profiles" / name).read_text())
+            v = tr.get(workload, {}).get(kernel, {}).get("bytes_per_launch")
+            if v is not None:
+                return v
+        except Exception:
+            continue
+    return None
+
+
+def measure_workload(args, workload, per_gpu, dev, rank, world, local, sample_clocks=True):
+    """One workload, whole protocol: build, (graph) capture, W warm-up steps, K timed steps, K end-to-end
+    steps, one instrumented step for the per-kernel roofline.  Returns the record (rank 0) or None."""
+    from mirage_b200 import ops
+    size, mods, _, kind = WORKLOADS[workload]
     sys.path.insert(0, str(ROOT / "tests"))
     from helpers import load_synth, synth_images
-
+    extra = {}
+    graph_hooks = None
+    ddp = None
     if kind == "encoder":
         from mirage_b200.mirage_hf import MIRAGEWrapper
         model = MIRAGEWrapper(size=size, modalities="-".join(mods))
@@ -246,94 +272,80 @@ def run_gpu(args):
         def step_eager():
             with torch.no_grad():
                 return model(dev_in)
-        step = step_eager
 
         def step_e2e():
             # public host-to-host call: pinned inputs -> encoder -> pinned output, copies overlapped
             # with compute chunk by chunk (mirage_hf.MIRAGEWrapper.encode_host)
-            return model.encode_host(host_in, out=host_out, chunk=args.e2e_chunk, ramp=args.e2e_ramp)
+            return model.encode_host(host_in, out=host_out, chunk=args.e2e_chunk,
+                                     ramp=min(args.e2e_ramp, max(1, per_gpu // 8)))
         h2d = sum(v.numel() * v.element_size() for v in host_in.values())
         d2h = host_out.numel() * host_out.element_size()
-        flop_per_sample = GFLOP_FWD[args.workload] * 1e9
+        flop_per_sample = GFLOP_FWD[workload] * 1e9
         unit = "images/s"
     elif kind == "cls":
         from bench_support import build_cls_step
-        step, step_e2e, h2d, d2h = build_cls_step(size, per_gpu, dev, rank, world)
-        step_eager = step
-        graph_hooks = None
-        flop_per_sample = 3.0 * GFLOP_FWD[args.workload] * 1e9
+        step_eager, step_e2e, h2d, d2h, graph_hooks, ddp = build_cls_step(size, per_gpu, dev, rank, world, args)
+        flop_per_sample = 3.0 * GFLOP_FWD[workload] * 1e9
         unit = "samples/s"
     else:
         from bench_support import build_pretrain_step
-        step, step_e2e, h2d, d2h, graph_hooks = build_pretrain_step(size, mods, per_gpu, dev, rank, world)
-        step_eager = step
-        flop_per_sample = 3.0 * GFLOP_FWD[args.workload] * 1e9
+        step_eager, step_e2e, h2d, d2h, graph_hooks, ddp = build_pretrain_step(size, mods, per_gpu, dev, rank,
+                                                                               world, args)
+        flop_per_sample = 3.0 * GFLOP_FWD[workload] * 1e9
         unit = "samples/s"
+    step = step_eager
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # whole-step CUDA graph (falls back to eager launches when capture is not possible)
     graphed = False
     if args.graph:
         try:
             if kind == "encoder":
                 from mirage_b200.graphs import GraphedCallable
-                gstep = GraphedCallable(step_eager).capture()
-                step = gstep
+                step = GraphedCallable(step_eager, refresh_weights=False).capture()
                 graphed = True
-            elif world == 1 and graph_hooks is not None:
+            elif graph_hooks is not None:
                 step, step_e2e = graph_hooks()
                 graphed = True
         except Exception as e:  # noqa: BLE001
             if rank == 0:
-                print(f"bench.py: CUDA-graph capture failed ({type(e).__name__}: {e}); eager launches",
-                      file=sys.stderr, flush=True)
+                print(f"bench.py: CUDA-graph capture of {workload} failed ({type(e).__name__}: {e}); "
+                      "eager launches", file=sys.stderr, flush=True)
             torch.cuda.synchronize()
             step = step_eager
 
     W, K = max(3, args.warmup), max(1, args.steps)
     for _ in range(W):
         step()
-    sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local) if (rank == 0 and sample_clocks) else None
+    if sampler:
         sampler.start()
-    ops.reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    for _ in range(K):
-        step()
-    e1.record()
-    sync_all()
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_total = _timed(step, K, world, dev)
+    clocks = sampler.stop() if sampler else None
 
-    # end-to-end through the public API with host buffers (H2D + D2H inside the timed region)
     for _ in range(2):
         step_e2e()
-    sync_all()
-    e0.record()
-    for _ in range(K):
-        step_e2e()
-    e1.record()
-    sync_all()
-    ms_e2e = e0.elapsed_time(e1)
+    ms_e2e = _timed(step_e2e, K, world, dev)
 
-    if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = t.tolist()
+    # how much of the gradient exchange is NOT hidden behind backward: the same step with the all-reduce off
+    if ddp is not None and world > 1:
+        ddp.enabled = False
+        try:
+            quiet = step_eager
+            if graphed and graph_hooks is not None and args.mask_sampler == "device":
+                quiet, _ = graph_hooks()
+            for _ in range(2):
+                quiet()
+            ms_quiet = _timed(quiet, K, world, dev)
+            extra["allreduce_exposed_ms"] = round((ms_total - ms_quiet) / K, 3)
+            extra["ms_per_step_without_allreduce"] = round(ms_quiet / K, 3)
+        finally:
+            ddp.enabled = True
+        extra["allreduce_bytes_per_step"] = int(sum(b.flat.numel() * b.flat.element_size() for b in ddp.buckets))
+        extra["reserve_sms"] = ddp.reserve_sms
+    elif ddp is not None:
+        extra["allreduce_exposed_ms"] = 0.0
 
-    # per-kernel roofline pass: one more step with CUDA events around every launch (rank 0)
-    # (every rank runs the step -- the pretraining step contains the gradient all-reduce -- but only
-    # rank 0 records)
-    roofline = None
-    kernels = None
+    # per-kernel roofline pass: one more (eager) step with CUDA events around every launch; every rank runs it
+    # (the training step contains the collective), rank 0 records
     kt = KernelTimer()
     if rank == 0:
         ops.set_recorder(kt)
@@ -341,67 +353,127 @@ def run_gpu(args):
     step_eager()
     torch.cuda.synchronize()
     ops.set_recorder(None)
-    # kernels of libmirage_b200.so launched inside the timed region: counted on one eager step (a graph
-    # replay launches the same kernels without passing through the Python counter) times K
     launches = ops.launch_count() * K
-    if rank == 0:
-        agg = kt.summary()
-        peaks = measured_peaks()
-        tot = sum(a["ms"] for a in agg.values()) or 1.0
-        kernels = {k: {"ms": round(a["ms"], 3), "share": round(a["ms"] / tot, 3), "launches": a["launches"],
-                       ("tflops" if a["unit"] == "flop" else "gbs"):
-                           round(a["work"] / a["ms"] / (1e9 if a["unit"] == "flop" else 1e6), 1)}
-                   for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
-        top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-        name, a = top
-        traffic = None
-        try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture, if any
-            tr = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
-            traffic = tr.get(args.workload, {}).get(name, {}).get("bytes_per_launch")
-        except Exception:
-            traffic = None
-        if a["unit"] == "flop":
-            ach = a["work"] / a["ms"] / 1e9
-            peak = peaks["bf16_tflops_sustained"]
-            roofline = {"kernel": name, "bound": "tensor", "achieved": round(ach, 1), "peak": peak,
-                        "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
-                        "peak_source": peaks["source"] + " (sustained bf16)",
-                        "per_launch": {"flops": a["work"] / a["launches"], "ms": a["ms"] / a["launches"]}}
-        else:
-            ach = a["work"] / a["ms"] / 1e6
-            peak = peaks["hbm_gbs"]
-            roofline = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak,
-                        "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
-                        "peak_source": peaks["source"],
-                        "per_launch": {"bytes": a["work"] / a["launches"], "ms": a["ms"] / a["launches"]}}
+    _sync_all(world)
+    if rank != 0:
+        return None
+
+    peaks = measured_peaks()
+    agg = kt.summary()
+    tot = sum(a["ms"] for a in agg.values()) or 1.0
+    kernels = {k: {"ms": round(a["ms"], 3), "share": round(a["ms"] / tot, 3), "launches": a["launches"],
+                   ("tflops" if a["unit"] == "flop" else "gbs"):
+                       round(a["work"] / a["ms"] / (1e9 if a["unit"] == "flop" else 1e6), 1)}
+               for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+    name, a = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    traffic = _traffic_entry(workload, name)
+    if a["unit"] == "flop":
+        ach = a["work"] / a["ms"] / 1e9
+        peak = peaks["bf16_tflops_sustained"]
+        roofline = {"kernel": name, "bound": "tensor", "achieved": round(ach, 1), "peak": peak,
+                    "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
+                    "peak_source": peaks["source"] + " (sustained bf16)",
+                    "per_launch": {"flops": a["work"] / a["launches"], "ms": a["ms"] / a["launches"]}}
+    else:
+        ach = a["work"] / a["ms"] / 1e6
+        peak = peaks["hbm_gbs"]
+        roofline = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak,
+                    "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
+                    "peak_source": peaks["source"],
+                    "per_launch": {"bytes": a["work"] / a["launches"], "ms": a["ms"] / a["launches"]}}
+    total = per_gpu * world * K
+    value = total / (ms_total / 1e3)
+    rec = {
+        "metric": f"{workload} {unit}", "value": round(value, 2), "unit": unit, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": round(ms_total / K, 3),
+        "config": {"workload": workload, "size": size, "modalities": mods, "per_gpu_batch": per_gpu,
+                   "global_batch": per_gpu * world,
+                   "parallelism": f"dp{world} (batch-sharded, no collective)" if kind == "encoder"
+                   else f"dp{world} (NCCL gradient all-reduce overlapped with backward)",
+                   "l2_policy": "inputs_exceed_l2 (activations >> 126 MB per step)", "cuda_graph": graphed},
+        "model_tflops": round(value * flop_per_sample / 1e12, 1),
+        "model_frac_of_bf16_peak": round(value * flop_per_sample / 1e12 / world / peaks["bf16_tflops"], 4),
+        "roofline": roofline, "kernels": kernels,
+        "e2e": {"value": round(total / (ms_e2e / 1e3), 2), "unit": unit, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if kind != "encoder":
+        rec["config"]["optimizer"] = args.optimizer
+        rec["config"]["mask_sampler"] = args.mask_sampler if kind == "pretrain" else None
+    rec.update(extra)
+    return rec
+
+
+def _free_gpu():
+    import gc
+    from mirage_b200 import functional as Fn
+    Fn.set_grad_sink(None)
+    Fn.drop_cast_cache()
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the MIRAGE hot path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        if args.nccl_max_ctas > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_max_ctas))
+        dist.init_process_group("nccl", device_id=dev)
+
+    # default invocation = both halves of BASELINE.json's metric: the MIRAGE-L encoder (headline line) and
+    # the MultiMAE pretraining step (sub-record "pretrain"), plus the strong-scaling encoder point of SURVEY 8(d)
+    # (global batch 256 split over the ranks) when there is more than one rank
+    default = args.workload == "default"
+    head_name = "encoder_large" if default else args.workload
+    per_gpu = args.batch or WORKLOADS[head_name][2]
+    head = measure_workload(args, head_name, per_gpu, dev, rank, world, local)
+    subs = {}
+    if default:
+        if world > 1 and not args.skip_strong:
+            _free_gpu()
+            subs["encoder_strong"] = measure_workload(args, "encoder_large", max(1, 256 // world), dev, rank, world,
+                                                      local, sample_clocks=False)
+        if not args.skip_pretrain:
+            _free_gpu()
+            subs["pretrain"] = measure_workload(args, "pretrain_large", args.batch or WORKLOADS["pretrain_large"][2],
+                                                dev, rank, world, local)
 
     if rank == 0:
-        total = per_gpu * world * K
-        value = total / (ms_total / 1e3)
-        e2e_v = total / (ms_e2e / 1e3)
         cpu = None
+        unit = head["unit"]
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, desc = cpu_oracle_throughput(args.workload, budget_s=15.0, batch=2)
+            v, cores, desc = cpu_oracle_throughput(head_name, budget_s=15.0, batch=2)
             cpu = {"value": round(v, 3), "unit": unit, "cores": cores, "kind": "port", "sample": desc}
-        peaks = measured_peaks()
         line = {
-            "metric": f"{args.workload} {unit}", "value": round(value, 2), "unit": unit,
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 3),
+            "metric": head["metric"], "value": head["value"], "unit": unit, "n_gpus": world,
+            "steps": head["steps"], "warmup": head["warmup"], "ms_per_step": head["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
-            "config": {"workload": args.workload, "size": size, "modalities": mods,
-                       "per_gpu_batch": per_gpu, "global_batch": per_gpu * world,
-                       "parallelism": f"dp{world} (batch-sharded, no collective)" if kind == "encoder"
-                       else f"dp{world} (NCCL gradient all-reduce)",
-                       "l2_policy": "inputs_exceed_l2 (activations >> 126 MB per step)",
-                       "cuda_graph": graphed},
-            "model_tflops": round(value * flop_per_sample / 1e12, 1),
-            "model_frac_of_bf16_peak": round(value * flop_per_sample / 1e12 / world / peaks["bf16_tflops"], 4),
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
-            "e2e": {"value": round(e2e_v, 2), "unit": unit, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": clocks,
+            "data": "synthetic", "config": head["config"],
+            "model_tflops": head["model_tflops"], "model_frac_of_bf16_peak": head["model_frac_of_bf16_peak"],
+            "roofline": head["roofline"], "kernels": head["kernels"], "cpu_baseline": cpu, "e2e": head["e2e"],
+            "gpu_launches": head["gpu_launches"] + sum(r["gpu_launches"] for r in subs.values() if r),
+            "clocks": head["clocks"],
         }
+        for k in ("allreduce_exposed_ms", "ms_per_step_without_allreduce", "allreduce_bytes_per_step", "reserve_sms"):
+            if k in head:
+                line[k] = head[k]
+        for name, r in subs.items():
+            if r is None:
+                continue
+            r = dict(r)
+            r["scaling"] = "strong" if name == "encoder_strong" else "weak"
+            r["dtype"], r["data"] = "bf16", "synthetic"
+            line[name] = r
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -415,7 +487,24 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="encoder_large", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="default", choices=["default"] + sorted(WORKLOADS),
+                    help="default = encoder_large headline + pretrain_large (+ encoder_strong when N > 1)")
+    ap.add_argument("--skip-pretrain", action="store_true", help="default workload: encoder line only")
+    ap.add_argument("--skip-strong", action="store_true", help="default workload: no strong-scaling encoder point")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="training steps: optim.FusedAdamW (csrc/optim.cu) or torch.optim.AdamW(fused=True)")
+    ap.add_argument("--mask-sampler", default="device", choices=["device", "reference"],
+                    help="pretraining: fused on-device mask sampling kernel or the reference's op sequence")
+    ap.add_argument("--bucket-mb", type=float, default=64.0, help="gradient all-reduce bucket size")
+    ap.add_argument("--linear-probe", action="store_true",
+                    help="cls_large: only head.* trains (fm_cls_config.py:111-124)")
+    ap.add_argument("--label-smoothing", type=float, default=0.0,
+                    help="cls_large: label-smoothing cross entropy (run_cls_tuning.py:438-441)")
+    ap.add_argument("--reserve-sms", type=int, default=-1,
+                    help="SMs kept free of persistent compute CTAs while gradient buckets are in flight "
+                         "(-1 = auto: 8 when N > 1)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=-1,
+                    help="NCCL_MAX_CTAS for the gradient all-reduce (-1 = auto: same as --reserve-sms, 0 = leave)")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel eagerly")
@@ -425,8 +514,15 @@ def main():
     ap.add_argument("--e2e-ramp", type=int, default=18, help="images in the first and last (short) chunk")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload == "default":
+            args.workload = "encoder_large"
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    n = max(world, args.gpus)
+    if args.reserve_sms < 0:
+        args.reserve_sms = 8 if n > 1 else 0
+    if args.nccl_max_ctas < 0:
+        args.nccl_max_ctas = args.reserve_sms
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

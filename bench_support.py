@@ -1,5 +1,6 @@
-"""Pretraining workloads for bench.py (cfg 3 / cfg 4 of BASELINE.json): model + criteria + AdamW +
-gradient all-reduce on the GPU arm, and the oracle's forward+backward on the CPU arm."""
+"""Training workloads for bench.py (cfg 3 / 4 / 5 of BASELINE.json): model + criteria + optimizer step +
+gradient all-reduce on the GPU arm, and the oracle's forward+backward on the CPU arm (which imports
+nothing from the product package)."""
 from __future__ import annotations
 
 import sys
@@ -11,7 +12,52 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT / "tests"))
 
 
-def build_pretrain_step(size, mods, per_gpu, dev, rank, world):
+def _make_optimizer(model, ddp, lr, opts, skip=()):
+    """AdamW over the reference's parameter groups (mutils/optim_factory.py:33-92): 1-D tensors, biases and the
+    model's no_weight_decay() names undecayed; beta = (0.9, 0.95), wd 0.05 (run_pretraining.py:172,189)."""
+    from mirage_b200.optim import FusedAdamW, get_parameter_groups
+    groups = get_parameter_groups(model, 0.05, skip)
+    if opts.optimizer == "fused":
+        return FusedAdamW(groups, lr=lr, betas=(0.9, 0.95), zero_grad_in_step=True,
+                          grad_buckets=[b.flat for b in ddp.buckets])
+    return torch.optim.AdamW(groups, lr=lr, betas=(0.9, 0.95), fused=True, capturable=True)
+
+
+def _schedule(lr, steps=4096):
+    from mirage_b200.optim import cosine_scheduler
+    return cosine_scheduler(lr, 0.0, 1, steps, warmup_epochs=0), cosine_scheduler(0.05, 0.05, 1, steps)
+
+
+def _train_step_factory(model, ddp, opt, opts, loss_fn):
+    """Returns one_step(x): zero / forward / loss / backward (+ bucketed all-reduce) / optimizer step."""
+    fused = opts.optimizer == "fused"
+
+    def one_step(x):
+        ddp.zero_grad(memset=not fused)       # FusedAdamW zeroes the buckets inside its own update pass
+        loss = loss_fn(x)
+        loss.backward()
+        ddp.finish()
+        opt.step()
+        return loss
+    return one_step
+
+
+def _host_schedule(opt, opts, lr):
+    """The per-step lr / weight-decay assignment of run_pretraining.py:683-688 (host side, every step)."""
+    from mirage_b200.optim import assign_step_hyper
+    lr_sched, wd_sched = _schedule(lr)
+    state = {"it": 0}
+
+    def tick():
+        it = state["it"] % len(lr_sched)
+        state["it"] += 1
+        assign_step_hyper(opt, it, lr_sched, wd_sched)
+        if opts.optimizer == "fused":
+            opt.refresh_hyper()
+    return tick
+
+
+def build_pretrain_step(size, mods, per_gpu, dev, rank, world, opts):
     from helpers import load_synth, synth_images
     from mirage_b200.ddp import GradBucketAllReduce
     from pretrain_case import build_criteria, build_pretrain_model
@@ -19,16 +65,13 @@ def build_pretrain_step(size, mods, per_gpu, dev, rank, world):
     model, _ = build_pretrain_model(size, mods)
     load_synth(model, seed=3)
     model = model.to(dev).train()
+    if opts.mask_sampler == "device":
+        model.set_mask_sampler("device", seed=4242 + rank)
     crits = build_criteria(mods)
-    ddp = GradBucketAllReduce(model, bucket_mb=64)
-    decay, no_decay = [], []
-    skip = model.no_weight_decay()
-    for n, p in model.named_parameters():
-        if not p.requires_grad:
-            continue
-        (no_decay if (p.ndim <= 1 or n.endswith(".bias") or n in skip) else decay).append(p)
-    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}],
-                            lr=1e-4 * per_gpu * world / 256, betas=(0.9, 0.95), fused=True, capturable=True)
+    ddp = GradBucketAllReduce(model, bucket_mb=opts.bucket_mb, reserve_sms=opts.reserve_sms if world > 1 else 0)
+    lr = 1e-4 * per_gpu * world / 256
+    opt = _make_optimizer(model, ddp, lr, opts, model.no_weight_decay())
+    tick = _host_schedule(opt, opts, lr)
 
     base = synth_images(8, mods, seed=1234 + rank)
     reps = per_gpu // 8 + 1
@@ -37,47 +80,51 @@ def build_pretrain_step(size, mods, per_gpu, dev, rank, world):
     torch.manual_seed(100 + rank)
     host_loss = torch.zeros(1).pin_memory()
 
-    def one_step(x):
-        ddp.zero_grad()
+    def loss_fn(x):
         preds, masks = model(x, num_encoded_tokens=98, alphas=1.0, sample_tasks_uniformly=False)
-        loss = sum(crits[d](preds[d].float(), x[d], mask=masks[d]) for d in mods)
-        loss.backward()
-        ddp.finish()
-        opt.step()
-        return loss
+        return sum(crits[d](preds[d].float(), x[d], mask=masks[d]) for d in mods)
+    one_step = _train_step_factory(model, ddp, opt, opts, loss_fn)
 
     def step():
+        tick()
         return one_step(dev_in)
 
     def step_e2e():
+        tick()
         x = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
         loss = one_step(x)
         host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
 
     def graph_hooks():
-        """Whole-step CUDA graph (single rank): forward + losses + backward + AdamW are captured once;
-        the token masks are sampled eagerly every step exactly as the reference does (CPU Dirichlet +
-        device noise, mirage/model.py:168-239) and copied into the fixed tensors the graph reads."""
+        """Whole-step CUDA graph: forward + losses + backward (+ the NCCL all-reduce of every bucket, which
+        torch captures as cross-stream dependencies) + the optimizer step are captured once.  With the
+        on-device mask sampler the masks are drawn INSIDE the graph (the kernel advances its own Philox
+        counter); with the reference sampler they are drawn eagerly before every replay exactly as the
+        reference does (CPU Dirichlet + device noise, mirage/model.py:168-239) and copied into the fixed
+        tensors the graph reads."""
         from mirage_b200.graphs import GraphedCallable
-        sampler = model.generate_random_masks
-        toks = {d: torch.empty(per_gpu, 256, 0, device=dev) for d in mods}
-        tm0, keep0, restore0 = sampler(toks, 98, alphas=1.0)
-        fixed = ({d: t.clone() for d, t in tm0.items()}, keep0.clone(), restore0.clone())
         x_fixed = {k: v.clone() for k, v in dev_in.items()}
+        resample = None
+        if opts.mask_sampler != "device":
+            sampler = model.generate_random_masks
+            toks = {d: torch.empty(per_gpu, 256, 0, device=dev) for d in mods}
+            tm0, keep0, restore0 = sampler(toks, 98, alphas=1.0)
+            fixed = ({d: t.clone() for d, t in tm0.items()}, keep0.clone(), restore0.clone())
 
-        def resample():
-            tm, keep, restore = sampler(toks, 98, alphas=1.0)
-            for d in mods:
-                fixed[0][d].copy_(tm[d])
-            fixed[1].copy_(keep)
-            fixed[2].copy_(restore)
-
-        model.generate_random_masks = lambda *a, **k: fixed
-        g = GraphedCallable(lambda: one_step(x_fixed)).capture()
+            def resample():
+                tm, keep, restore = sampler(toks, 98, alphas=1.0)
+                for d in mods:
+                    fixed[0][d].copy_(tm[d])
+                fixed[1].copy_(keep)
+                fixed[2].copy_(restore)
+            model.generate_random_masks = lambda *a, **k: fixed
+        g = GraphedCallable(lambda: one_step(x_fixed), refresh_weights=opts.optimizer != "fused").capture()
 
         def gstep():
-            resample()
+            tick()
+            if resample is not None:
+                resample()
             return g()
 
         # end-to-end leg: the batch of step k+1 travels host -> device (pinned memory, side stream) while
@@ -103,65 +150,96 @@ def build_pretrain_step(size, mods, per_gpu, dev, rank, world):
             for k in x_fixed:
                 x_fixed[k].copy_(staging[k], non_blocking=True)
             prefetch(main.record_event())          # next step's batch, overlapped with this step
-            resample()
+            tick()
+            if resample is not None:
+                resample()
             loss = g()
             host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
             return loss
         return gstep, gstep_e2e
 
     h2d = sum(v.numel() * v.element_size() for v in host_in.values())
-    return step, step_e2e, h2d, 4, graph_hooks
+    return step, step_e2e, h2d, 4, graph_hooks, ddp
 
 
-def build_cls_step(size, per_gpu, dev, rank, world):
-    """cfg 5: miragecls_factory['global'] full fine-tune step (forward + CE + backward + gradient
-    exchange + AdamW), bscan 512x512, 5 classes."""
+def build_cls_step(size, per_gpu, dev, rank, world, opts):
+    """cfg 5: miragecls_factory['global'] fine-tune step (forward + CE + backward + gradient exchange + AdamW),
+    bscan 512x512, 5 classes.  ``opts.linear_probe``: only ``head.*`` trains
+    (fm_cls_config.py:111-124)."""
     from cls_case import build_cls_model
     from helpers import synth_images
     from mirage_b200.ddp import GradBucketAllReduce
     model, _ = build_cls_model("global", 21, device=dev, size=size)
     model.train()
-    ddp = GradBucketAllReduce(model, bucket_mb=64)
-    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.05,
-                            fused=True)
+    if opts.mask_sampler == "device":
+        model.model.set_mask_sampler("device", seed=777 + rank)
+    if getattr(opts, "linear_probe", False):
+        for n, p in model.named_parameters():
+            p.requires_grad_(n.startswith("head."))
+    ddp = GradBucketAllReduce(model, bucket_mb=opts.bucket_mb, reserve_sms=opts.reserve_sms if world > 1 else 0)
+    opt = _make_optimizer(model, ddp, 1e-4, opts)
+    tick = _host_schedule(opt, opts, 1e-4)
     base = synth_images(8, ["bscan"], seed=1234 + rank)["bscan"]
     host_x = base.repeat(per_gpu // 8 + 1, 1, 1, 1)[:per_gpu].contiguous().pin_memory()
     dev_x = host_x.to(dev)
     tgt = torch.randint(0, 5, (per_gpu,), generator=torch.Generator().manual_seed(5 + rank)).to(dev)
     torch.manual_seed(100 + rank)
     host_loss = torch.zeros(1).pin_memory()
+    smoothing = float(getattr(opts, "label_smoothing", 0.0))
 
-    def one_step(x):
-        ddp.zero_grad()
-        loss = torch.nn.functional.cross_entropy(model(x).float(), tgt)
-        loss.backward()
-        ddp.finish()
-        opt.step()
-        return loss
+    def loss_fn(x):
+        return torch.nn.functional.cross_entropy(model(x).float(), tgt, label_smoothing=smoothing)
+    one_step = _train_step_factory(model, ddp, opt, opts, loss_fn)
 
     def step():
+        tick()
         return one_step(dev_x)
 
     def step_e2e():
+        tick()
         loss = one_step(host_x.to(dev, non_blocking=True))
         host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
-    return step, step_e2e, host_x.numel() * 4, 4
+
+    def graph_hooks():
+        """Whole-step CUDA graph (needs the on-device mask sampler: the cls wrappers draw a random token
+        permutation every forward)."""
+        if opts.mask_sampler != "device":
+            raise RuntimeError("cls step capture needs --mask-sampler device")
+        from mirage_b200.graphs import GraphedCallable
+        x_fixed = dev_x.clone()
+        g = GraphedCallable(lambda: one_step(x_fixed), refresh_weights=opts.optimizer != "fused").capture()
+
+        def gstep():
+            tick()
+            return g()
+
+        def gstep_e2e():
+            tick()
+            x_fixed.copy_(host_x, non_blocking=True)
+            loss = g()
+            host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+            return loss
+        return gstep, gstep_e2e
+    return step, step_e2e, host_x.numel() * 4, 4, graph_hooks, ddp
 
 
+# ---------------------------------------------------------------------------------------------
+# CPU legs (oracle only: no product import)
+# ---------------------------------------------------------------------------------------------
 def build_cls_oracle(size, batch, seed):
-    from cls_case import build_cls_model, oracle_cls_logits
-    from helpers import synth_images
-    _, sd = build_cls_model("global", 21, size=size)
+    from helpers import synth_images, synth_state_dict
+    from oracle import mirage_oracle as O
+    sd = O.cls_state_dict_shapes(size)
+    sd.update(synth_state_dict({k: v.shape for k, v in sd.items()}, 21))
     leaf = {k: v.clone().requires_grad_(not k.endswith("pos_emb")) for k, v in sd.items()}
     x = synth_images(batch, ["bscan"], seed=1234)["bscan"]
     tgt = torch.arange(batch) % 5
-    depth_heads = (12, 12) if size == "base" else (24, 16)
+    _, depth, heads = O.MODEL_SIZES[size]
 
     def run():
-        from oracle import mirage_oracle as O
         msd = {k[len("model."):]: v for k, v in leaf.items() if k.startswith("model.")}
-        tok = O.light_forward({"bscan": x}, msd, *depth_heads)
+        tok = O.light_forward({"bscan": x}, msd, depth, heads)
         loss = torch.nn.functional.cross_entropy(O.cls_head(tok, leaf, "global"), tgt)
         loss.backward()
         for v in leaf.values():
@@ -172,13 +250,19 @@ def build_cls_oracle(size, batch, seed):
 
 def build_pretrain_oracle(size, mods, batch, seed):
     from helpers import synth_images, synth_state_dict
-    from pretrain_case import build_pretrain_model, oracle_step, sample_masks
-    model, _ = build_pretrain_model(size, mods)
-    sd = model.state_dict()
+    from oracle import mirage_oracle as O
+    sd = O.pretrain_state_dict_shapes(mods, size)
     sd.update(synth_state_dict({k: v.shape for k, v in sd.items()}, 3))
     x = synth_images(batch, mods, seed=1234)
-    masks = sample_masks(model, batch, 98, seed=100)
+    torch.manual_seed(100)
+    tm, keep, restore = O.random_masks([256] * len(mods), batch, 98, alphas=1.0)
+    task_masks = dict(zip(mods, tm))
+    _, depth, heads = O.MODEL_SIZES[size]
 
     def run():
-        return oracle_step(sd, x, masks, size, mods)
+        leaf = {k: v.clone().requires_grad_(not k.endswith("pos_emb")) for k, v in sd.items()}
+        preds, _ = O.pretrain_forward(x, leaf, depth, heads, (None, keep, restore), mods)
+        total, _losses = O.pretrain_loss(preds, x, task_masks)
+        total.backward()
+        return total
     return run

@@ -29,7 +29,11 @@ extern "C" {
 /* ---------------------------------------------------------------- runtime ------------------ */
 const char* mb_last_error(void);
 int mb_version(void);
-int mb_sm_count(void);
+int mb_sm_count(void);          /* SMs the persistent kernels size their grids to (physical - reserve) */
+/* Keep `n` SMs free of persistent CTAs (GEMM, attention, LayerNorm backward size their grids to the rest), so
+ * that communication kernels running concurrently (the NCCL gradient all-reduce launched from inside backward)
+ * find SMs without waiting for -- or delaying -- a whole compute wave.  Returns the previous value. */
+int mb_set_sm_reserve(int n);
 void mb_clear_tensor_map_cache(void);
 
 /* ---------------------------------------------------------------- GEMM --------------------- */

@@ -922,11 +922,10 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
     p.stagger = stagger;
   }
   auto kern = attn_fwd_kernel<HD, POLY>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     MB_CHECK_CUDA(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
   }
   const long long items = (long long)p.B * p.H * p.q_pairs;
   MB_REQUIRE(items > 0 && items < (1ll << 31), "mb_attn_fwd: %lld work items out of range", items);
@@ -939,11 +938,10 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
       // when that still fills the machine several times over
       if (p.H % 4 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && (long long)p.B * (p.H / 4) >= 4ll * sm_count()) {
         const size_t tsmem = (size_t)(4 * ((p.Nk + 3) & ~3) + 4 * HD + 16 * HD + 8) * sizeof(float);
-        static bool tail_configured = false;
-        if (!tail_configured) {
+        static PerDeviceOnce tail_configured;
+        if (tail_configured.first()) {
           MB_CHECK_CUDA(cudaFuncSetAttribute(attn_tail_rows4_kernel<HD>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 + 16 * 1024));
-          tail_configured = true;
         }
         attn_tail_rows4_kernel<HD><<<(unsigned)(p.B * (p.H / 4)), kTailThreads, tsmem, stream>>>(p);
       } else {

@@ -452,11 +452,10 @@ static int launch_attn_bwd(const mb_attn_bwd_args* a, cudaStream_t stream) {
   MB_REQUIRE(p.kv_blocks == 1 || a->workspace != nullptr,
              "mb_attn_bwd: nk > 128 needs a workspace of mb_attn_bwd_workspace() bytes");
   auto kern = attn_bwd_kernel<HD>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     MB_CHECK_CUDA(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
   }
   const long long items = (long long)p.B * p.H;
   const long long grid = items < sm_count() ? items : sm_count();  // persistent CTAs

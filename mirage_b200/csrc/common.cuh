@@ -720,6 +720,22 @@ int make_tensor_map(CUtensorMap* out, const void* base, TmaDtype dtype, int rank
                     const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                     int swizzle_bytes = 128);
 
+// SMs persistent kernels may occupy on the current device: the physical count minus what
+// mb_set_sm_reserve() keeps free for concurrently running communication kernels (NCCL).
 int sm_count();
+
+// "do this once per device" (cudaFuncSetAttribute is a per-device setting): first() is true the first time
+// it is called with a given current device.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return true;
+    d &= 63;
+    const bool was = done[d];
+    done[d] = true;
+    return !was;
+  }
+};
 
 }  // namespace mb200

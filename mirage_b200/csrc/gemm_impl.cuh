@@ -723,11 +723,10 @@ int launch_gemm_single(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<BN, A_LAYOUT, B_MN, ESIZE, EPI>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     MB_CHECK_CUDA(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
   }
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
@@ -740,11 +739,10 @@ int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev
                      cudaStream_t stream) {
   using Cfg = PairCfg<BN>;
   auto kern = gemm_pair_kernel<BN, A_LAYOUT, B_MN, ESIZE, EPI>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     MB_CHECK_CUDA(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
   }
   const int max_clusters = sm_count() / 2;
   const int clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;

@@ -23,17 +23,26 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int sm_count() {
-  static int cached = 0;
+static int g_sm_physical[64] = {};
+static int g_sm_reserve = 0;
+
+static int sm_physical() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& cached = g_sm_physical[dev & 63];
   if (cached == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       return 148;
     cached = n;
   }
   return cached;
+}
+
+int sm_count() {
+  int n = sm_physical() - g_sm_reserve;
+  n &= ~1;  // CTA pairs
+  return n < 2 ? 2 : n;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -149,6 +158,12 @@ const char* mb_last_error(void) { return mb200::g_last_error; }
 int mb_version(void) { return MB_VERSION; }
 
 int mb_sm_count(void) { return mb200::sm_count(); }
+
+int mb_set_sm_reserve(int n) {
+  const int prev = mb200::g_sm_reserve;
+  mb200::g_sm_reserve = n < 0 ? 0 : n;
+  return prev;
+}
 
 void mb_clear_tensor_map_cache(void) {
   std::lock_guard<std::mutex> lk(mb200::g_map_mu);

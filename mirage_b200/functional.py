@@ -121,13 +121,8 @@ def _as_bf16(t: torch.Tensor) -> torch.Tensor:
     return ops.cast_bf16(t.contiguous())
 
 
-_SMS = [0]
-
-
 def _sm_count() -> int:
-    if _SMS[0] == 0:
-        _SMS[0] = int(L.lib().mb_sm_count())
-    return _SMS[0]
+    return int(L.lib().mb_sm_count())   # follows mb_set_sm_reserve
 
 
 def _wgrad_splits(n_out: int, k_in: int, tokens: int) -> int:

@@ -368,3 +368,75 @@ def cls_head(tokens: Tensor, sd: Dict[str, Tensor], pool: str = "global", n_glob
     glob = t[:, -n_global:].mean(dim=1)
     feat = {"global": patch, "cls": glob, "token_mix": torch.cat([patch, glob], dim=1)}[pool]
     return feat @ sd["head.weight"].t() + sd["head.bias"]
+
+
+# --------------------------------------------------------------------------------------------
+# reference-compatible state_dict layouts (SURVEY.md 8(b) "state_dict keys"), built WITHOUT the product
+# package: bench.py's CPU legs and the tests fill them with seeded synthetic weights.
+# --------------------------------------------------------------------------------------------
+MODEL_SIZES = {"tiny": (128, 2, 2), "base": (768, 12, 12), "large": (1024, 24, 16)}
+
+
+def _block_keys(sd: Dict[str, Tensor], pre: str, dim: int, ratio: int = 4):
+    """Block parameter layout, mirage/utils.py:236-257 (+ Attention :167-174, Mlp :143-151)."""
+    z = torch.zeros
+    sd[pre + "norm1.weight"], sd[pre + "norm1.bias"] = torch.ones(dim), z(dim)
+    sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"] = z(3 * dim, dim), z(3 * dim)
+    sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"] = z(dim, dim), z(dim)
+    sd[pre + "norm2.weight"], sd[pre + "norm2.bias"] = torch.ones(dim), z(dim)
+    sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"] = z(ratio * dim, dim), z(ratio * dim)
+    sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"] = z(dim, ratio * dim), z(dim)
+
+
+def light_state_dict_shapes(mods: Sequence[str], size: str, grid: Tuple[int, int] = (16, 16)) -> Dict[str, Tensor]:
+    """Encoder-only (MIRAGELight / hf MIRAGEWrapper.model) state_dict: zero weights of the right shapes and the
+    real frozen sin-cos ``pos_emb`` tables (input_adapters.py:66-72; model.py:61-87)."""
+    dim, depth, _ = MODEL_SIZES[size]
+    sd: Dict[str, Tensor] = {"global_tokens": torch.zeros(1, 1, dim)}
+    for d in mods:
+        pre = f"input_adapters.{d}."
+        sd[pre + "pos_emb"] = sincos_posemb_2d(grid[0], grid[1], dim)
+        if d == "bscanlayermap":
+            sd[pre + "class_emb.weight"] = torch.zeros(13, 64)
+            sd[pre + "proj.weight"], sd[pre + "proj.bias"] = torch.zeros(dim, 64, 8, 8), torch.zeros(dim)
+        else:
+            sd[pre + "proj.weight"], sd[pre + "proj.bias"] = torch.zeros(dim, 1, 32, 32), torch.zeros(dim)
+    for i in range(depth):
+        _block_keys(sd, f"encoder.{i}.", dim)
+    return sd
+
+
+def pretrain_state_dict_shapes(mods: Sequence[str], size: str, dec_dim: int = 256, dec_depth: int = 2,
+                               grid: Tuple[int, int] = (16, 16)) -> Dict[str, Tensor]:
+    """MIRAGEModel + one SpatialOutputAdapter per task (output_adapters.py:50-145)."""
+    dim = MODEL_SIZES[size][0]
+    sd = light_state_dict_shapes(mods, size, grid)
+    z = torch.zeros
+    for d in mods:
+        pre = f"output_adapters.{d}."
+        sd[pre + "mask_token"] = z(1, 1, dec_dim)
+        sd[pre + "pos_emb"] = sincos_posemb_2d(grid[0], grid[1], dec_dim)
+        for t in mods:
+            sd[f"{pre}task_embeddings.{t}"] = z(1, 1, dec_dim)
+        sd[pre + "decoder.q.weight"], sd[pre + "decoder.q.bias"] = z(dec_dim, dec_dim), z(dec_dim)
+        sd[pre + "decoder.kv.weight"], sd[pre + "decoder.kv.bias"] = z(2 * dec_dim, dec_dim), z(2 * dec_dim)
+        sd[pre + "decoder.proj.weight"], sd[pre + "decoder.proj.bias"] = z(dec_dim, dec_dim), z(dec_dim)
+        for n in ("context_norm", "query_norm", "out_norm"):
+            sd[f"{pre}{n}.weight"], sd[f"{pre}{n}.bias"] = torch.ones(dec_dim), z(dec_dim)
+        sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"] = z(4 * dec_dim, dec_dim), z(4 * dec_dim)
+        sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"] = z(dec_dim, 4 * dec_dim), z(dec_dim)
+        for j in range(dec_depth):
+            _block_keys(sd, f"{pre}decoder_transformer.{j}.", dec_dim)
+        out = (13 * 8 * 8) if d == "bscanlayermap" else 32 * 32
+        sd[pre + "out_proj.weight"], sd[pre + "out_proj.bias"] = z(out, dec_dim), z(out)
+        sd[pre + "proj_context.weight"], sd[pre + "proj_context.bias"] = z(dec_dim, dim), z(dec_dim)
+    return sd
+
+
+def cls_state_dict_shapes(size: str, num_classes: int = 5, factor: int = 1) -> Dict[str, Tensor]:
+    """miragecls_factory[...] (mirage_wrapper.py:190-206): encoder under ``model.``, ``norm`` and ``head``."""
+    dim = MODEL_SIZES[size][0]
+    sd = {"model." + k: v for k, v in light_state_dict_shapes(["bscan"], size).items()}
+    sd["norm.weight"], sd["norm.bias"] = torch.ones(dim), torch.zeros(dim)
+    sd["head.weight"], sd["head.bias"] = torch.zeros(num_classes, dim * factor), torch.zeros(num_classes)
+    return sd
