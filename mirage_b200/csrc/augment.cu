@@ -5,8 +5,8 @@
 // :172-185), then ships fp32 images over PCIe.  Here the RAW uint8 batch travels (4x fewer bytes) and one
 // gather kernel per modality applies, in the reference's order:
 //     uint8 -> [0,1] float (:178)  ->  horizontal flip (:43-44)  ->  intensity shift + clip (:45-50, images only)
-//     ->  affine warp, bilinear, zero fill (:54-67; torchvision F.affine on tensors = affine_grid +
-//         grid_sample(align_corners=False))  ->  nearest resize of the layer map to its input size (:68-78)
+//     ->  affine warp, bilinear, fill 0 (:54-67; torchvision F.affine on tensors = affine_grid +
+//         grid_sample(align_corners=False, zeros padding) times the equally warped all-ones mask)  ->  nearest resize of the layer map to its input size (:68-78)
 // The per-sample parameters (flip, shift, inverse affine matrix in torchvision's centred convention) are
 // drawn on the host and passed as a small table, so the random stream stays the caller's business.
 //
@@ -28,8 +28,12 @@ struct AugRow {
 
 template <bool LABELS>
 __device__ __forceinline__ float aug_fetch(const uint8_t* __restrict__ img, int H, int W, int y, int x, bool flip,
-                                           float shift) {
-  if (x < 0 || x >= W || y < 0 || y >= H) return 0.f;  // fill = 0
+                                           float shift, float& inside) {
+  if (x < 0 || x >= W || y < 0 || y >= H) {  // grid_sample padding_mode = zeros
+    inside = 0.f;
+    return 0.f;
+  }
+  inside = 1.f;
   const uint8_t raw = img[y * W + (flip ? W - 1 - x : x)];
   if (LABELS) return static_cast<float>(raw);
   return fminf(fmaxf(static_cast<float>(raw) / 255.0f + shift, 0.f), 1.f);
@@ -39,7 +43,8 @@ template <bool LABELS>
 __device__ __forceinline__ float aug_sample(const uint8_t* __restrict__ img, int H, int W, float ox, float oy,
                                             const AugRow& r, bool identity) {
   const bool flip = r.flip != 0.f;
-  if (identity) return aug_fetch<LABELS>(img, H, W, static_cast<int>(oy), static_cast<int>(ox), flip, r.shift);
+  float i00, i01, i10, i11;
+  if (identity) return aug_fetch<LABELS>(img, H, W, static_cast<int>(oy), static_cast<int>(ox), flip, r.shift, i00);
   const float cx = 0.5f * (W - 1), cy = 0.5f * (H - 1);
   const float dx = ox - cx, dy = oy - cy;
   const float px = r.m00 * dx + r.m01 * dy + r.m02 + cx;
@@ -47,12 +52,17 @@ __device__ __forceinline__ float aug_sample(const uint8_t* __restrict__ img, int
   const float fx = floorf(px), fy = floorf(py);
   const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
   const float wx = px - fx, wy = py - fy;
-  const float v00 = aug_fetch<LABELS>(img, H, W, y0, x0, flip, r.shift);
-  const float v01 = aug_fetch<LABELS>(img, H, W, y0, x0 + 1, flip, r.shift);
-  const float v10 = aug_fetch<LABELS>(img, H, W, y0 + 1, x0, flip, r.shift);
-  const float v11 = aug_fetch<LABELS>(img, H, W, y0 + 1, x0 + 1, flip, r.shift);
+  const float v00 = aug_fetch<LABELS>(img, H, W, y0, x0, flip, r.shift, i00);
+  const float v01 = aug_fetch<LABELS>(img, H, W, y0, x0 + 1, flip, r.shift, i01);
+  const float v10 = aug_fetch<LABELS>(img, H, W, y0 + 1, x0, flip, r.shift, i10);
+  const float v11 = aug_fetch<LABELS>(img, H, W, y0 + 1, x0 + 1, flip, r.shift, i11);
   // grid_sample's bilinear form: sum of the four corner values times their area weights
-  return v00 * ((1.f - wx) * (1.f - wy)) + v01 * (wx * (1.f - wy)) + v10 * ((1.f - wx) * wy) + v11 * (wx * wy);
+  const float w00 = (1.f - wx) * (1.f - wy), w01 = wx * (1.f - wy), w10 = (1.f - wx) * wy, w11 = wx * wy;
+  const float val = v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11;
+  // torchvision's fill handling (F_t._apply_grid_transform): a channel of ones is warped along with the image and
+  // the result is img * mask + (1 - mask) * fill -- with fill = 0 the border is attenuated TWICE
+  const float mask = i00 * w00 + i01 * w01 + i10 * w10 + i11 * w11;
+  return val * mask;
 }
 
 __device__ __forceinline__ bool aug_is_identity(const AugRow& r) {

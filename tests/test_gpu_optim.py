@@ -73,8 +73,9 @@ def test_fused_adamw_matches_torch(mode):
     assert int(our.step_count.item()) == expected_steps
     for (pa, pb) in zip(our_m.parameters(), ref_m.parameters()):
         sa, sb = our.state[pa], ref.state[pb]
-        assert torch.allclose(sa["exp_avg"], sb["exp_avg"], rtol=1e-5, atol=1e-9)
-        assert torch.allclose(sa["exp_avg_sq"], sb["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+        for key in ("exp_avg", "exp_avg_sq"):   # same tolerance as the parameters: relative to the tensor's scale
+            err = (sa[key] - sb[key]).abs().max().item()
+            assert err <= 2e-6 * sb[key].abs().max().item(), (key, err)
 
 
 def test_fused_adamw_refreshes_bf16_twins_and_zeroes_grads():
