@@ -29,11 +29,11 @@ def report(name, got, ref, tol=2e-2):
     return ok
 
 
-def attn_case(B, H, nq, nk, hd, self_attn=True):
+def attn_case(B, H, nq, nk, hd, self_attn=True, amp=1.0):
     D = H * hd
     scale = hd ** -0.5
     if self_attn:
-        qkv = (torch.randn(B * nq, 3 * D, device=dev) * 1.0).bfloat16()
+        qkv = (torch.randn(B * nq, 3 * D, device=dev) * amp).bfloat16()
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
     else:
         q = torch.randn(B * nq, D, device=dev).bfloat16()
@@ -47,7 +47,7 @@ def attn_case(B, H, nq, nk, hd, self_attn=True):
     vf = v.float().reshape(B, nk, H, hd).transpose(1, 2)
     s = (qf @ kf.transpose(-1, -2)) * scale
     ref = (torch.softmax(s, -1) @ vf).transpose(1, 2).reshape(B * nq, D)
-    ok = report(f"attn B={B} H={H} nq={nq} nk={nk} hd={hd}", out, ref)
+    ok = report(f"attn B={B} H={H} nq={nq} nk={nk} hd={hd} amp={amp}", out, ref)
     ok &= report("   lse", lse, torch.logsumexp(s, -1), tol=1e-3)
     return ok
 
@@ -74,6 +74,12 @@ def group_attn64():
     ok &= attn_case(40, 16, 257, 257, 64)
     ok &= attn_case(64, 16, 99, 99, 64)
     ok &= attn_case(20, 16, 514, 514, 64)                  # two peeled rows: separate tail kernel
+    # large score range: the lazy running-max rescale of O in TMEM fires (four-tile kernel and two-tile kernel)
+    ok &= attn_case(3, 4, 513, 513, 64, amp=3.0)
+    ok &= attn_case(2, 4, 1025, 1025, 64, amp=4.0)
+    ok &= attn_case(3, 4, 257, 257, 64, amp=3.0)
+    ok &= attn_case(2, 2, 2049, 2049, 64)
+    ok &= attn_case(300, 16, 513, 513, 64)                 # > 2 waves of (batch, head) items per CTA
     # enough (batch, head-group) CTAs for the four-heads-per-CTA tail kernel
     ok &= attn_case(160, 16, 257, 257, 64)
     ok &= attn_case(200, 12, 130, 130, 64)
