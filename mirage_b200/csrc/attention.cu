@@ -752,7 +752,14 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
       use_v4 = e ? atoi(e) : 1;
     }
     if (use_v4) {
-      const int rc = launch_attn_fwd4(a, p, POLY, stream);
+      // a quarter of the exponentials on the FMA pipe (exp2_poly2) pays off in the four-tile kernel (0.57 -> 0.51 ms
+      // at cfg 2) although it never did in the two-tile kernel below (MB_ATTN_POLY overrides both)
+      static int poly4 = -1;
+      if (poly4 < 0) {
+        const char* e = getenv("MB_ATTN_POLY");
+        poly4 = e ? atoi(e) : 4;
+      }
+      const int rc = launch_attn_fwd4(a, p, poly4, stream);
       if (rc < 0) return rc;
       main_done = (rc == 0);
     }

@@ -30,6 +30,19 @@
 
 namespace mb200 {
 
+constexpr int kA4GroupsDbg = 4;
+#ifdef MB_ATTN4_TIMING
+// debug build only (MB_NVCC_EXTRA=-DMB_ATTN4_TIMING): SM-clock timestamps of CTA 0, key blocks [kT0, kT0 + kTN)
+constexpr int kT0 = 100, kTN = 6, kTE = 12;
+__device__ long long g_a4_t[kTN][kA4GroupsDbg][4][kTE];
+#define A4_T(blk, g, q, e)                                                                   \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && (blk) >= kT0 && (blk) < kT0 + kTN) g_a4_t[(blk) - kT0][g][q][e] = clock64(); \
+  } while (0)
+#else
+#define A4_T(blk, g, q, e) do { } while (0)
+#endif
+
 constexpr int kA4Threads = 896;     // 7 warpgroups: {TMA, MMA x3}, {MMA, -, -, -}, 4 x softmax, epilogue
 constexpr int kA4Groups = 4;
 constexpr int kA4KvStages = 4;
@@ -52,6 +65,49 @@ struct A4Cfg {
 };
 static_assert(A4Cfg::kSmemBytes <= 227 * 1024, "attention4 shared memory exceeds the 227 KB per-CTA limit");
 
+// One 64-column score row in registers -> packed bf16 exponentials in sreg[0..32), returns their sum and (e_max)
+// their maximum.  Three passes in pinned program order as exp_row (attention_common.cuh): x = s * scale - m
+// (FFMA2), e = 2^x in place (MUFU back to back), then sum (FADD2, four chains) + maximum (FMNMX, four chains)
+// + bf16 packing.
+//
+// Tried and rejected (all measured on B200, cfg 2): pacing the MUFU passes of the four softmax warps
+// of an SM sub-partition so that they do not bunch -- a token ring per sub-partition (1.14 ms with one token,
+// 0.82-0.84 ms with two to four, vs 0.56 ms unpaced), a FIFO ticket lock making the pass exclusive (0.62 vs 0.60
+// ms), and issuing the MMAs from thread 0 of the softmax warpgroup behind a named barrier instead of a dedicated
+// issuer warp (0.64 ms).  scripts/micro/mufu_rate.cu shows why pacing cannot help: the MUFU is shared fairly and
+// one warp alone already sustains 97 % of its rate, so the pass length is not the limiter.
+template <int POLY>
+__device__ __forceinline__ float exp_row_max(uint32_t (&sreg)[64], float scale_log2, float neg_m, float& e_max) {
+#pragma unroll
+  for (int i = 0; i < 64; i += 2) ffma2_v(sreg[i], sreg[i + 1], scale_log2, neg_m);
+#pragma unroll
+  for (int i = 0; i < 64; i += 2) {
+    if (((i >> 1) * POLY) / 16 != (((i >> 1) + 1) * POLY) / 16) {
+      float e0, e1;
+      exp2_poly2(e0, e1, __uint_as_float(sreg[i]), __uint_as_float(sreg[i + 1]));
+      sreg[i] = __float_as_uint(e0);
+      sreg[i + 1] = __float_as_uint(e1);
+    } else {
+      ex2_v(sreg[i]);
+      ex2_v(sreg[i + 1]);
+    }
+  }
+  float sum[8], mx[4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) sum[a] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) mx[a] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; i += 2) {
+    const int a = (i >> 1) & 3;
+    fadd2_v(sum[2 * a], sum[2 * a + 1], sreg[i], sreg[i + 1]);
+    mx[a] = fmaxf(mx[a], fmaxf(__uint_as_float(sreg[i]), __uint_as_float(sreg[i + 1])));
+    sreg[i >> 1] = pack_bf16x2(__uint_as_float(sreg[i]), __uint_as_float(sreg[i + 1]));
+  }
+  e_max = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+  return ((sum[0] + sum[1]) + (sum[2] + sum[3])) + ((sum[4] + sum[5]) + (sum[6] + sum[7]));
+}
+
 template <int POLY>
 __global__ void __launch_bounds__(kA4Threads, 1)
 attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -70,7 +126,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint64_t* v_full = bars + 12;                 // 4
   uint64_t* v_empty = bars + 16;                // 4   4 commits
   uint64_t* s_full = bars + 20;                 // 4   MMA commit: S_g(j) complete (and P_g V(j-1) retired)
-  uint64_t* p_full = bars + 24;                 // 4   128 softmax threads: P_g(j) in TMEM
+  uint64_t* p_full = bars + 24;                 // 4   4 softmax warps (one elected lane each): P_g(j) in TMEM
   uint64_t* o_full = bars + 28;                 // 4   MMA commit: the item's last P_g V retired
   uint64_t* o_free = bars + 32;                 // 4   4 epilogue warps: O_g of the item read out
   uint64_t* stats_full = bars + 36;             // 4   128 softmax threads: row statistics of the item
@@ -107,7 +163,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
     for (int g = 0; g < kA4Groups; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&p_full[g], 128);
+      mbar_init(&p_full[g], 4);
       mbar_init(&o_full[g], 1);
       mbar_init(&o_free[g], 4);
       mbar_init(&stats_full[g], 128);
@@ -161,73 +217,94 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           tma_load_3d(smem + Cfg::kOffV + s * Cfg::kKvTile, &tm_v, &v_full[s], h * HD, j * kA4Block, b);
         }
       }
-    } else if (warp >= 1 && warp <= kA4Groups && lane == 0) {
+    } else if (warp >= 1 && warp <= kA4Groups) {
       // -------------------------------------------------------------- MMA issuer of query tile g
       // Event order of one tile: S(0) | P(0) -> PV(0), S(1) | P(1) -> PV(1), S(2) | ...  S_g and P_g alias in
       // TMEM, and MMAs issued by one thread execute in order, so S(j+1) lands only after P V(j) has read P(j).
       // The next item's S(0) is issued right behind this item's last P V (its Q sits in the other slot).
-      const int g = warp - 1;
+      //
+      // The softmax warps wait for the whole P(j) -> [P V(j), S(j+1)] round trip, so this path is kept short:
+      //   * the WHOLE warp runs the loop (converged) and every address is derived from shuffled, i.e. provably
+      //     warp-uniform, values: the MMA operands then live in uniform registers.  The first version ran
+      //     under `lane == 0` with per-thread values, and ptxas wrapped every tcgen05.mma in an ELECT /
+      //     R2UR.BROADCAST / BRA.U.ANY loop: ~100 clk per MMA, 1150-1400 clk from "P ready" to "S committed"
+      //     (clock64 timeline, scripts/attn4_timeline.py);
+      //   * everything that does not depend on P(j) -- V(j) / K(j+1) / next Q arrival, O_g drained -- is waited
+      //     for BEFORE p_full, and all descriptors are formed before it too.
+      const int g = __shfl_sync(0xffffffffu, warp, 0) - 1;
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const bool leader = elect_one();
       const uint32_t q_addr = smem_u32(smem + Cfg::kOffQ);
       const uint32_t k_addr = smem_u32(smem + Cfg::kOffK);
       const uint32_t v_addr = smem_u32(smem + Cfg::kOffV);
-      const uint32_t t_s = tmem_base + g * 64;
-      const uint32_t t_o = tmem_base + 256 + g * 64;
+      const uint32_t t_s = tb + g * 64;
+      const uint32_t t_o = tb + 256 + g * 64;
       constexpr uint32_t idesc_s = make_idesc(128, kA4Block, kFmtBF16, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(128, HD, kFmtBF16, 0, 1);
       int pc = 0;  // P V MMAs issued (phase of p_full)
       int oc = 0;  // items finished  (phase of o_free)
 
-      auto issue_s = [&](int item_i, int kc, bool last_of_item) {
+      // S(it, block kc): caller has made sure Q(it) is resident
+      auto issue_s = [&](int it, int kc, bool last_of_item, bool wait_k) {
         const int s = kc % kA4KvStages;
-        mbar_wait(&k_full[s], (kc / kA4KvStages) & 1);
-        tc_fence_after();
-        const uint32_t qa = q_addr + ((item_i & 1) * kA4Groups + g) * Cfg::kQTile;
-        const uint32_t ka = k_addr + s * Cfg::kKvTile;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_f16_ss(t_s, make_smem_desc(qa + k * 32, 0, kSbo, kSw), make_smem_desc(ka + k * 32, 0, kSbo, kSw),
-                      idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&s_full[g]);
-        umma_commit(&k_empty[s]);
-        if (last_of_item) umma_commit(&q_empty[item_i & 1]);
-      };
-      auto issue_pv = [&](int j, int kc) {
-        const int s = kc % kA4KvStages;
-        mbar_wait(&p_full[g], pc & 1);
-        if (j == 0 && oc > 0) mbar_wait(&o_free[g], (oc - 1) & 1);  // previous item's O read out
-        mbar_wait(&v_full[s], (kc / kA4KvStages) & 1);
-        tc_fence_after();
-        const uint32_t va = v_addr + s * Cfg::kKvTile;
-#pragma unroll
-        for (int kk = 0; kk < kA4Block / 16; ++kk)
-          umma_f16_ts(t_o, t_s + kk * 8, make_smem_desc(va + kk * 16 * 128, 0, kSbo, kSw), idesc_pv,
-                      (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&v_empty[s]);
-        ++pc;
-        if (j == kvb - 1) {
-          umma_commit(&o_full[g]);
-          ++oc;
+        if (wait_k) {
+          mbar_wait(&k_full[s], (kc / kA4KvStages) & 1);
+          tc_fence_after();
         }
+        const uint64_t qd = make_smem_desc(q_addr + ((it & 1) * kA4Groups + g) * Cfg::kQTile, 0, kSbo, kSw);
+        const uint64_t kd = make_smem_desc(k_addr + s * Cfg::kKvTile, 0, kSbo, kSw);
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)   // +32 bytes per K step = +2 in the descriptor's 16-byte address field
+            umma_f16_ss(t_s, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+          umma_commit(&k_empty[s]);
+          if (last_of_item) umma_commit(&q_empty[it & 1]);
+        }
+        __syncwarp();
       };
 
       int kv_base = 0, item_i = 0;
-      bool s0_issued = false;
+      if (blockIdx.x < n_items) {
+        mbar_wait(&q_full[0], 0);
+        issue_s(0, 0, false, true);
+      }
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i, kv_base += kvb) {
-        if (!s0_issued) {
-          mbar_wait(&q_full[item_i & 1], (item_i >> 1) & 1);
-          issue_s(item_i, kv_base, kvb == 1);
-        }
-        s0_issued = false;
-        const int next = item + gridDim.x;
+        const bool has_next = item + static_cast<int>(gridDim.x) < n_items;
         for (int j = 0; j < kvb; ++j) {
-          issue_pv(j, kv_base + j);
-          if (j + 1 < kvb) {
-            issue_s(item_i, kv_base + j + 1, j + 1 == kvb - 1);
-          } else if (next < n_items) {
-            mbar_wait(&q_full[(item_i + 1) & 1], ((item_i + 1) >> 1) & 1);
-            issue_s(item_i + 1, kv_base + kvb, kvb == 1);
-            s0_issued = true;
+          const int kc = kv_base + j;
+          const int sv = kc % kA4KvStages;
+          const bool last = (j == kvb - 1);
+          // --- not on the critical path: operands of the two MMA groups
+          mbar_wait(&v_full[sv], (kc / kA4KvStages) & 1);
+          if (!last || has_next) {
+            if (last) mbar_wait(&q_full[(item_i + 1) & 1], ((item_i + 1) >> 1) & 1);
+            mbar_wait(&k_full[(kc + 1) % kA4KvStages], ((kc + 1) / kA4KvStages) & 1);
           }
+          if (j == 0 && oc > 0) mbar_wait(&o_free[g], (oc - 1) & 1);  // previous item's O read out
+          const uint64_t vd = make_smem_desc(v_addr + sv * Cfg::kKvTile, 0, kSbo, kSw);
+          A4_T(pc, g, 0, 2);
+          // --- critical path: P(j) ready -> P V(j) -> S(j+1)
+          mbar_wait(&p_full[g], pc & 1);
+          tc_fence_after();
+          A4_T(pc, g, 0, 1);
+          if (leader) {
+#pragma unroll
+            for (int kk = 0; kk < kA4Block / 16; ++kk)   // 16 keys = 2048 bytes = +128 in the address field
+              umma_f16_ts(t_o, t_s + kk * 8, vd + 128 * kk, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(&v_empty[sv]);
+            if (last) umma_commit(&o_full[g]);
+          }
+          __syncwarp();
+          A4_T(pc, g, 0, 3);
+          ++pc;
+          if (last) ++oc;
+          if (!last) {
+            issue_s(item_i, kc + 1, j + 1 == kvb - 1, false);
+          } else if (has_next) {
+            issue_s(item_i + 1, kc + 1, false, false);
+          }
+          A4_T(pc - 1, g, 0, 5);
         }
       }
     }
@@ -285,52 +362,81 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       for (int j = 0; j < kvb; ++j, ++cnt) {
         mbar_wait(&s_full[g], cnt & 1);   // S_g(j) complete; P_g V(j-1) retired (O_g stable, P_g free)
         tc_fence_after();
+        if (lane == 0) A4_T(cnt, g, quarter, 6);
         uint32_t sreg[64];
         tmem_ld_32x32b_x32_p(t_s, sreg);
         tmem_ld_32x32b_x32_p(t_s + 32, sreg + 32);
         tmem_ld_wait();
+        if (lane == 0) A4_T(cnt, g, quarter, 7);
 
-        float mxh[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) mxh[a] = fmaxf(__uint_as_float(sreg[a]), __uint_as_float(sreg[a + 8]));
-#pragma unroll
-        for (int i = 16; i < 64; i += 16) {
-#pragma unroll
-          for (int a = 0; a < 8; ++a)
-            mxh[a] = fmaxf(mxh[a], fmaxf(__uint_as_float(sreg[i + a]), __uint_as_float(sreg[i + a + 8])));
-        }
-        float mx_row = fmaxf(fmaxf(fmaxf(mxh[0], mxh[1]), fmaxf(mxh[2], mxh[3])),
-                             fmaxf(fmaxf(mxh[4], mxh[5]), fmaxf(mxh[6], mxh[7])));
-        if (j == kvb - 1) {
-#pragma unroll
-          for (int t = 0; t < kA4MaxTail; ++t) mx_row = fmaxf(mx_row, s_tail[t]);  // -inf when unused
-        }
-        const float m_cand = fmaxf(m_run, mx_row * p.scale_log2);
+        // Running max, lazily: m_run is fixed by the first block and moves only when a later block exceeds it by
+        // more than 2^8 (the final O / l does not depend on the reference point, and P <= 256 is well inside
+        // bf16 / fp32 range).  Blocks j > 0 are therefore exponentiated SPECULATIVELY against the stale m_run
+        // without looking for their maximum first -- that search (~400 clk incl. the vote, clock64 timeline) sat
+        // on the per-block critical path; now the maximum is taken over the exponentials in the summation pass
+        // (FMNMX on the ALU pipe, next to the FADD2 / pack instructions) and only a warp that finds one above
+        // 2^8 (or inf) takes the slow path: reload S_g from TMEM (still intact: P_g is stored afterwards),
+        // move m_run, rescale l and O_g, exponentiate again.
         if (j == 0) {
-          m_run = m_cand;  // nothing accumulated yet: P V(0) overwrites O
-        } else if (__any_sync(0xffffffffu, m_cand > m_run + kLazyMaxLog2)) {
-          // lazy rescale (rare, warp-uniform): O_g is stable here, see the wait above
-          const float alpha = fast_exp2(m_run - m_cand);
-          l_run *= alpha;
-          m_run = m_cand;
-#pragma unroll 1
-          for (int c = 0; c < HD / 16; ++c) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(t_o + c * 16, v);
-            tmem_ld_wait();
+          float mxh[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_32x32b_x16(t_o + c * 16, v);
+          for (int a = 0; a < 8; ++a) mxh[a] = fmaxf(__uint_as_float(sreg[a]), __uint_as_float(sreg[a + 8]));
+#pragma unroll
+          for (int i = 16; i < 64; i += 16) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+              mxh[a] = fmaxf(mxh[a], fmaxf(__uint_as_float(sreg[i + a]), __uint_as_float(sreg[i + a + 8])));
           }
+          m_run = fmaxf(fmaxf(fmaxf(mxh[0], mxh[1]), fmaxf(mxh[2], mxh[3])),
+                        fmaxf(fmaxf(mxh[4], mxh[5]), fmaxf(mxh[6], mxh[7]))) * p.scale_log2;
         }
-        const float neg_m = -m_run;
-        float sum = exp_row<true, POLY>(sreg, p.scale_log2, neg_m, 64, 2);
+        if (lane == 0) A4_T(cnt, g, quarter, 8);
+        float e_max;
+        float sum = exp_row_max<POLY>(sreg, p.scale_log2, -m_run, e_max);
         if (j == kvb - 1) {
 #pragma unroll
           for (int t = 0; t < kA4MaxTail; ++t) {
-            e_tail[t] = fast_exp2(fmaf(s_tail[t], p.scale_log2, neg_m));  // exp2(-inf) = 0
-            sum += e_tail[t];
+            e_tail[t] = fast_exp2(fmaf(s_tail[t], p.scale_log2, -m_run));  // exp2(-inf) = 0
+            e_max = fmaxf(e_max, e_tail[t]);
           }
+        }
+        if (__any_sync(0xffffffffu, !(e_max <= 256.f))) {
+          // slow path (rare, warp-uniform)
+          tmem_ld_32x32b_x32_p(t_s, sreg);
+          tmem_ld_32x32b_x32_p(t_s + 32, sreg + 32);
+          tmem_ld_wait();
+          float mx_row = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) mx_row = fmaxf(mx_row, __uint_as_float(sreg[i]));
+          if (j == kvb - 1) {
+#pragma unroll
+            for (int t = 0; t < kA4MaxTail; ++t) mx_row = fmaxf(mx_row, s_tail[t]);  // -inf when unused
+          }
+          const float m_new = fmaxf(m_run, mx_row * p.scale_log2);
+          if (j > 0) {  // (j == 0 lands here only through the tail key of a two-block item)
+            const float alpha = fast_exp2(m_run - m_new);
+            l_run *= alpha;
+#pragma unroll 1
+            for (int c = 0; c < HD / 16; ++c) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(t_o + c * 16, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st_32x32b_x16(t_o + c * 16, v);
+            }
+          }
+          m_run = m_new;
+          sum = exp_row_max<POLY>(sreg, p.scale_log2, -m_run, e_max);
+          if (j == kvb - 1) {
+#pragma unroll
+            for (int t = 0; t < kA4MaxTail; ++t) e_tail[t] = fast_exp2(fmaf(s_tail[t], p.scale_log2, -m_run));
+          }
+        }
+        if (lane == 0) A4_T(cnt, g, quarter, 9);
+        if (j == kvb - 1) {
+#pragma unroll
+          for (int t = 0; t < kA4MaxTail; ++t) sum += e_tail[t];
         }
         l_run += sum;
         // P_g(j): 64 bf16 = 32 columns, written over the first half of S_g (this thread's own lane)
@@ -338,7 +444,9 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_st_32x32b_x16_p(t_s + 16, sreg + 16);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_full[g]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);   // one arrival per warp: 128 per-thread arrivals serialise on the word
+        if (lane == 0) A4_T(cnt, g, quarter, 0);
       }
 
       // row statistics for the epilogue warps (double-buffered by item parity)
@@ -478,3 +586,9 @@ int launch_attn_fwd4(const mb_attn_args* a, const AttnDev& p_in, int poly, cudaS
 }
 
 }  // namespace mb200
+
+#ifdef MB_ATTN4_TIMING
+extern "C" int mb_debug_attn4_timing(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, mb200::g_a4_t, sizeof(mb200::g_a4_t)) == cudaSuccess ? 0 : -1;
+}
+#endif
