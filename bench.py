@@ -502,7 +502,7 @@ def main():
                     help="cls_large: label-smoothing cross entropy (run_cls_tuning.py:438-441)")
     ap.add_argument("--reserve-sms", type=int, default=-1,
                     help="SMs kept free of persistent compute CTAs while gradient buckets are in flight "
-                         "(-1 = auto: 8 when N > 1)")
+                         "(-1 = auto: 16 when N > 1; measured at N = 2: exposed all-reduce 3.7 / 1.9 / 1.4 ms with 0 / 8 / 16)")
     ap.add_argument("--nccl-max-ctas", type=int, default=-1,
                     help="NCCL_MAX_CTAS for the gradient all-reduce (-1 = auto: same as --reserve-sms, 0 = leave)")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
@@ -520,7 +520,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n = max(world, args.gpus)
     if args.reserve_sms < 0:
-        args.reserve_sms = 8 if n > 1 else 0
+        args.reserve_sms = 16 if n > 1 else 0
     if args.nccl_max_ctas < 0:
         args.nccl_max_ctas = args.reserve_sms
     if args.gpus > 1 and world == 1:

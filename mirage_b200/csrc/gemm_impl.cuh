@@ -437,8 +437,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  // The producer and the MMA issuer run as WHOLE, converged warps on warp-uniform values (loop counters, kernel
+  // parameters, shuffled registers) and elect one lane only around the TMA / MMA / commit instructions themselves.
+  // Under the previous `lane == 0` guard ptxas could not prove the operands uniform and wrapped every UTCHMMA and
+  // UTMALDG in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: ~100 clk of serial issue per MMA (clock64 timeline of
+  // the attention issuer, profiles/r02_ncu_attn_fwd4_summary.txt), i.e. ~400 clk per 64-wide K block against the
+  // 512 clk the four MMAs of that block take on the tensor core -- the issuer was nearly co-critical.
+  if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -447,9 +454,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int n0 = t.n_blk * BN;
       for (int kb = t.kb0; kb < t.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
+        if (leader) {
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
         if constexpr (A_LAYOUT == MB_MAJOR_K) {
           tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m0);
         } else if constexpr (A_LAYOUT == MB_MAJOR_MN) {
@@ -469,14 +477,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int s = 0; s < BN / 64; ++s)
             tma_load_2d(sb + s * 8192, &tma_b, &full_bar[stage], n0 + s * 64, kb * 64);
         }
+        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    const bool leader = elect_one();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     constexpr uint32_t idesc =
         make_idesc(kBM, BN, ESIZE == 2 ? kFmtBF16 : kFmtTF32, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
     constexpr uint32_t a_lbo = A_MN ? 8192u : 0u;
@@ -491,29 +503,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const TileCoord t = decode_tile(p, tile);
       mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc_stage * BN;
+      const uint32_t tmem_d = tmem_u + acc_stage * BN;
       for (int kb = t.kb0; kb < t.kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint32_t b_addr = a_addr + Cfg::kABytes;
+        // K step k = start address + k * kstep bytes = + k * (kstep >> 4) in the descriptor's address field
+        const uint64_t da0 = make_smem_desc(a_addr, a_lbo, 1024);
+        const uint64_t db0 = make_smem_desc(b_addr, b_lbo, 1024);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = make_smem_desc(a_addr + k * a_kstep, a_lbo, 1024);
-          const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024);
-          const uint32_t acc = (kb > t.kb0 || k > 0) ? 1u : 0u;
-          if constexpr (ESIZE == 2)
-            umma_f16_ss(tmem_d, da, db, idesc, acc);
-          else
-            umma_tf32_ss(tmem_d, da, db, idesc, acc);
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb > t.kb0 || k > 0) ? 1u : 0u;
+            if constexpr (ESIZE == 2)
+              umma_f16_ss(tmem_d, da0 + k * (a_kstep >> 4), db0 + k * (b_kstep >> 4), idesc, acc);
+            else
+              umma_tf32_ss(tmem_d, da0 + k * (a_kstep >> 4), db0 + k * (b_kstep >> 4), idesc, acc);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(&tmem_full_bar[acc_stage]);  // accumulator complete -> epilogue
+      if (leader) umma_commit(&tmem_full_bar[acc_stage]);  // accumulator complete -> epilogue
+      __syncwarp();
       acc_stage ^= 1;
       if (acc_stage == 0) acc_phase ^= 1;
     }
@@ -604,20 +621,24 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
+    // (whole warp, converged, uniform operands -- see gemm_kernel above)
+    const bool leader = elect_one();
+    const uint32_t cta_u = __shfl_sync(0xffffffffu, cta, 0);
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
       const TileCoord t = decode_tile(p, tile);  // m_tiles counts 256-row tiles here
-      const int m0 = t.m_blk * 256 + static_cast<int>(cta) * kBM;
-      const int n0 = t.n_blk * BN + static_cast<int>(cta) * (BN / 2);
+      const int m0 = t.m_blk * 256 + static_cast<int>(cta_u) * kBM;
+      const int n0 = t.n_blk * BN + static_cast<int>(cta_u) * (BN / 2);
       for (int kb = t.kb0; kb < t.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
         const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
+        if (leader) {
+        if (cta_u == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
         if constexpr (A_LAYOUT == MB_MAJOR_K) {
           tma_load_2d_pair(sa, &tma_a, fb, kb * BK, m0);
         } else if constexpr (A_LAYOUT == MB_MAJOR_MN) {
@@ -636,14 +657,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           for (int s = 0; s < BN / 128; ++s)
             tma_load_2d_pair(sb + s * 8192, &tma_b, fb, n0 + s * 64, kb * 64);
         }
+        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && cta == 0) {
-    // ------------------------------------------------------------------ MMA issuer (leader only)
+  } else if (warp == 1 && cta == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    const bool leader = elect_one();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     constexpr uint32_t idesc =
         make_idesc(256, BN, ESIZE == 2 ? kFmtBF16 : kFmtTF32, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
     constexpr uint32_t a_lbo = A_MN ? 8192u : 0u;
@@ -658,29 +683,33 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const TileCoord t = decode_tile(p, tile);
       mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc_stage * BN;
+      const uint32_t tmem_d = tmem_u + acc_stage * BN;
       for (int kb = t.kb0; kb < t.kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint32_t b_addr = a_addr + Cfg::kABytes;
+        const uint64_t da0 = make_smem_desc(a_addr, a_lbo, 1024);
+        const uint64_t db0 = make_smem_desc(b_addr, b_lbo, 1024);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = make_smem_desc(a_addr + k * a_kstep, a_lbo, 1024);
-          const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024);
-          const uint32_t acc = (kb > t.kb0 || k > 0) ? 1u : 0u;
-          if constexpr (ESIZE == 2)
-            umma_f16_ss_pair(tmem_d, da, db, idesc, acc);
-          else
-            umma_tf32_ss_pair(tmem_d, da, db, idesc, acc);
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb > t.kb0 || k > 0) ? 1u : 0u;
+            if constexpr (ESIZE == 2)
+              umma_f16_ss_pair(tmem_d, da0 + k * (a_kstep >> 4), db0 + k * (b_kstep >> 4), idesc, acc);
+            else
+              umma_tf32_ss_pair(tmem_d, da0 + k * (a_kstep >> 4), db0 + k * (b_kstep >> 4), idesc, acc);
+          }
+          umma_commit_pair(&empty_bar[stage]);
         }
-        umma_commit_pair(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit_pair(&tmem_full_bar[acc_stage]);
+      if (leader) umma_commit_pair(&tmem_full_bar[acc_stage]);
+      __syncwarp();
       acc_stage ^= 1;
       if (acc_stage == 0) acc_phase ^= 1;
     }
