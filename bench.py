@@ -282,6 +282,13 @@ def measure_workload(args, workload, per_gpu, dev, rank, world, local, sample_cl
         d2h = host_out.numel() * host_out.element_size()
         flop_per_sample = GFLOP_FWD[workload] * 1e9
         unit = "images/s"
+        # the same call fed with the RAW uint8 images (the on-disk format, scaled to [0, 1] on the device)
+        host_u8 = {k: (v * 255.0).round().to(torch.uint8).pin_memory() for k, v in host_in.items()}
+
+        def step_e2e_u8():
+            return model.encode_host(host_u8, out=host_out, chunk=args.e2e_chunk,
+                                     ramp=min(args.e2e_ramp, max(1, per_gpu // 8)))
+        extra["_e2e_u8"] = (step_e2e_u8, sum(v.numel() for v in host_u8.values()))
     elif kind == "cls":
         from bench_support import build_cls_step
         step_eager, step_e2e, h2d, d2h, graph_hooks, ddp = build_cls_step(size, per_gpu, dev, rank, world, args)
@@ -324,6 +331,12 @@ def measure_workload(args, workload, per_gpu, dev, rank, world, local, sample_cl
     for _ in range(2):
         step_e2e()
     ms_e2e = _timed(step_e2e, K, world, dev)
+    e2e_u8 = None
+    if "_e2e_u8" in extra:
+        fn, nbytes = extra.pop("_e2e_u8")
+        for _ in range(2):
+            fn()
+        e2e_u8 = (_timed(fn, K, world, dev), nbytes)
 
     # how much of the gradient exchange is NOT hidden behind backward: the same step with the all-reduce off
     if ddp is not None and world > 1:
@@ -399,6 +412,12 @@ def measure_workload(args, workload, per_gpu, dev, rank, world, local, sample_cl
                 "pcie_gbs_per_rank": round((h2d + d2h) / (ms_e2e / K / 1e3) / 1e9, 2)},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if e2e_u8 is not None:
+        ms_u8, nbytes = e2e_u8
+        rec["e2e_uint8_inputs"] = {"value": round(total / (ms_u8 / 1e3), 2), "unit": unit,
+                                   "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h,
+                                   "pcie_gbs_per_rank": round((nbytes + d2h) / (ms_u8 / K / 1e3) / 1e9, 2),
+                                   "note": "same public call, inputs as raw uint8 (scaled to [0,1] on the device)"}
     if kind != "encoder":
         rec["config"]["optimizer"] = args.optimizer
         rec["config"]["mask_sampler"] = args.mask_sampler if kind == "pretrain" else None
@@ -487,6 +506,8 @@ def run_gpu(args):
             "gpu_launches": head["gpu_launches"] + sum(r["gpu_launches"] for r in subs.values() if r),
             "clocks": head["clocks"], "host_binding": host_binding,
         }
+        if "e2e_uint8_inputs" in head:
+            line["e2e_uint8_inputs"] = head["e2e_uint8_inputs"]
         for k in ("allreduce_exposed_ms", "ms_per_step_without_allreduce", "allreduce_bytes_per_step", "reserve_sms"):
             if k in head:
                 line[k] = head[k]

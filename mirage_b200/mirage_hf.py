@@ -69,7 +69,10 @@ class MIRAGEWrapper(nn.Module):
     def encode_host(self, x: dict, out: torch.Tensor | None = None, chunk: int = 0, ramp: int = 18) -> torch.Tensor:
         """Batch inference from HOST tensors to a HOST tensor with the copies hidden behind compute.
 
-        x: {modality: pinned CPU [B, 1, H, W]}; out: pinned CPU [B, N_all + 1, D] fp32 (allocated when
+        x: {modality: pinned CPU [B, 1, H, W]}, fp32 in [0, 1] as the reference wrapper takes them, or RAW uint8
+        images (0..255, the on-disk format): those cross PCIe as bytes -- a quarter of the traffic -- and are
+        scaled to [0, 1] on the device (csrc/augment.cu with identity parameters = the reference's
+        ``image / 255``, mirage_wrapper.py:256-263).  out: pinned CPU [B, N_all + 1, D] fp32 (allocated when
         None).  The batch is walked in chunks on three streams -- H2D of chunk i+1, the encoder on chunk
         i, D2H of chunk i-1 -- with double-buffered device staging, so a step costs the encoder time
         plus one chunk of PCIe traffic instead of the whole batch's (new: the reference wrapper is a plain
@@ -120,7 +123,7 @@ class MIRAGEWrapper(nn.Module):
             if i + 1 < n_chunks:
                 load(i + 1)
             main.wait_event(ev_in[slot])
-            tok = self.model(staged[slot])
+            tok = self.model(self._to_unit_float(staged[slot]))
             keep.append(staged[slot])     # (see below: references instead of record_stream)
             ev_free[slot] = main.record_event()
             ev_tok = main.record_event()
@@ -136,6 +139,26 @@ class MIRAGEWrapper(nn.Module):
         # wait for the main stream), so the blocks can go back to their pools without record_stream().
         main.wait_stream(s_out)
         del keep
+        return out
+
+    def _to_unit_float(self, batch: dict) -> dict:
+        """uint8 device images -> fp32 [B, 1, H, W] in [0, 1]; fp32 inputs pass through."""
+        if all(v.dtype != torch.uint8 for v in batch.values()):
+            return batch
+        from . import ops
+        out = {}
+        for k, v in batch.items():
+            if v.dtype == torch.uint8:
+                u8 = v.reshape(v.shape[0], v.shape[-2], v.shape[-1]).contiguous()
+                ident = getattr(self, "_ident_params", None)
+                if ident is None or ident.shape[0] < u8.shape[0] or ident.device != u8.device:
+                    ident = torch.zeros((max(256, u8.shape[0]), 8), dtype=torch.float32, device=u8.device)
+                    ident[:, 2] = 1.0
+                    ident[:, 6] = 1.0
+                    self._ident_params = ident
+                out[k] = ops.augment_image(u8, ident[:u8.shape[0]])
+            else:
+                out[k] = v
         return out
 
     def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True, assign: bool = False):

@@ -158,6 +158,13 @@ def test_encode_host_pipeline_matches_forward():
         torch.cuda.synchronize()
         assert out.shape == ref.shape and out.is_pinned()
         assert_parity(out, ref, f"encode_host chunk={chunk}", max_rel=1e-5, cos=0.99999)
+    # raw uint8 inputs (the on-disk format) are scaled on the device exactly as `image / 255` on the host
+    u8 = {k: (v * 255).round().to(torch.uint8).pin_memory() for k, v in x.items()}
+    with torch.no_grad():
+        ref8 = m({k: (v.float() / 255.0).to(dev) for k, v in u8.items()})
+    out8 = m.encode_host(u8, chunk=3, ramp=1)
+    torch.cuda.synchronize()
+    assert_parity(out8, ref8, "encode_host uint8", max_rel=1e-5, cos=0.99999)
 
 
 @pytest.mark.parametrize("pool,size", [("global", "base"), ("cls", "base"), ("token_mix", "base"),
