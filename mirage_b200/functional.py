@@ -49,6 +49,9 @@ def bf16_weight(p: torch.Tensor) -> torch.Tensor:
     different, differently shaped parameter of a later model."""
     if p.dtype == torch.bfloat16:
         return p
+    if not isinstance(p, torch.nn.Parameter):
+        # a derived tensor (e.g. a zero-padded weight): nothing to key a persistent twin on
+        return ops.cast_bf16(p.detach().contiguous())
     key = id(p)
     ent = _shadow.get(key)
     if ent is not None and ent.ref() is p and ent.ptr == p.data_ptr() and ent.buf.shape == p.shape:
@@ -230,6 +233,19 @@ class _Linear(Function):
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
     return _Linear.apply(x, weight, bias, residual, out_f32, grad_needed(x, weight, bias, residual))
+
+
+# Linear with a narrow output (segmentation class logits): the GEMM wants N % 8 == 0, so weight and bias are
+# zero-padded to the next multiple of 8 rows (differentiably) and the extra columns are sliced off again.
+def linear_padded(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n = weight.shape[0]
+    pad = (-n) % 8
+    if pad:
+        weight = torch.cat([weight, weight.new_zeros(pad, weight.shape[1])], dim=0)
+        if bias is not None:
+            bias = torch.cat([bias, bias.new_zeros(pad)], dim=0)
+    y = linear(x, weight, bias, out_f32=True)
+    return y[:, :n] if pad else y
 
 
 # ---------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as Fn
+from .output_adapter_utils import ConvNeXtBlock
 from .utils import Block, CrossAttention, Mlp, build_2d_sincos_posemb, pair, trunc_normal_
 
 
@@ -165,3 +166,126 @@ class SpatialOutputAdapter(nn.Module):
                 x = blk.forward_flat(x, B, n_q)
         geom = (self.num_channels, self.P_H, self.P_W, N_H, N_W)
         return Fn.proj_unpatch(Fn.to_bf16(x), self.out_proj.weight, self.out_proj.bias, geom)
+
+
+# ---------------------------------------------------------------------------------------------
+# segmentation heads of the MIRAGELight / seg-tuning caller
+# ---------------------------------------------------------------------------------------------
+class Adapter(nn.Module):
+    """Token selection shared by the segmentation heads (mirage/output_adapters.py:299-322)."""
+
+    def __init__(self, main_tasks: Union[tuple, list] = ('bscan',)):
+        super().__init__()
+        self.main_tasks = main_tasks
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def adapt_tokens(self, encoder_tokens, input_info):
+        parts = [encoder_tokens[:, input_info['tasks'][t]['start_idx']:input_info['tasks'][t]['end_idx']]
+                 for t in self.main_tasks]
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
+
+    def _grid(self, input_info):
+        if self.image_size is None:
+            H, W = input_info['tasks'][self.task]['image_size']
+        else:
+            H, W = self.image_size
+        return H, W, H // self.patch_size[0], W // self.patch_size[1]
+
+
+def _token_matrix(x: torch.Tensor) -> torch.Tensor:
+    """[B, N, D] (possibly a slice of the encoder output) -> bf16 [B*N, D] GEMM operand."""
+    B, N, D = x.shape
+    return Fn.to_bf16(x.reshape(B * N, D).float().contiguous()) if x.dtype != torch.bfloat16 else x.reshape(B * N, D)
+
+
+class LinearSegAdapter(Adapter):
+    """One 1x1 conv on the patch tokens, then bilinear up-sampling (mirage/output_adapters.py:520-575).
+    The conv is a [B*N, D] x [D, classes] tcgen05 GEMM on the token matrix (class count padded to a multiple
+    of 8 columns inside ``functional.linear_padded``); ``F.interpolate`` stays a library call."""
+
+    def __init__(self, num_classes, main_tasks: Union[tuple, list] = ('bscan',),
+                 patch_size: Union[tuple, list] = [16, 16], interpolate_mode: str = 'bilinear',
+                 task: Optional[str] = None, image_size: Optional[Tuple[int, int]] = None, **kwargs):
+        super().__init__(main_tasks)
+        self.patch_size = patch_size
+        self.num_classes = num_classes
+        self.interpolate_mode = interpolate_mode
+        self.task = task
+        self.image_size = image_size
+        self.final_layer = nn.Identity()
+
+    def init(self, dim_tokens_enc: int = 768):
+        self.final_layer = nn.Conv2d(dim_tokens_enc, self.num_classes, 1)
+
+    def forward(self, encoder_tokens: torch.Tensor, input_info: Dict):
+        H, W, N_H, N_W = self._grid(input_info)
+        x = self.adapt_tokens(encoder_tokens, input_info)
+        B, N, D = x.shape
+        assert N == N_H * N_W
+        w = self.final_layer.weight.reshape(self.num_classes, D)
+        if x.is_cuda and D % 64 == 0:
+            y = Fn.linear_padded(_token_matrix(x), w, self.final_layer.bias)          # fp32 [B*N, classes]
+        else:
+            y = F.linear(x.reshape(B * N, D).float(), w, self.final_layer.bias)
+        y = y.reshape(B, N_H, N_W, self.num_classes).permute(0, 3, 1, 2)
+        return F.interpolate(y, size=(H, W), mode=self.interpolate_mode)
+
+
+class ConvNeXtAdapter(Adapter):
+    """Token projection -> sub-patch feature map -> ConvNeXt blocks -> 1x1 conv -> up-sampling
+    (mirage/output_adapters.py:437-517).  ``proj_dec``, the blocks' pointwise layers and ``final_layer`` run as
+    tcgen05 GEMMs; activations stay channels-last [B, H', W', C] between blocks."""
+
+    def __init__(self, num_classes, embed_dim: int = 6144, preds_per_patch: int = 16,
+                 main_tasks: Union[tuple, list] = ('bscan',), patch_size: list = [16, 16], depth: int = 4,
+                 interpolate_mode: str = 'bilinear', task: Optional[str] = None,
+                 image_size: Optional[Tuple[int, int]] = None, **kwargs):
+        super().__init__(main_tasks)
+        self.patch_size = patch_size
+        self.embed_dim = embed_dim
+        self.preds_per_patch = preds_per_patch
+        self.class_dim = embed_dim // preds_per_patch
+        self.num_classes = num_classes
+        self.interpolate_mode = interpolate_mode
+        self.task = task
+        self.image_size = image_size
+        self.blocks = nn.Sequential(*[ConvNeXtBlock(dim=self.class_dim) for _ in range(depth)])
+        self.final_layer = nn.Conv2d(self.class_dim, self.num_classes, 1)
+        self.apply(self._init_weights)
+
+    def init(self, dim_tokens_enc: int = 768):
+        self.in_channels = dim_tokens_enc * len(self.main_tasks)
+        self.proj_dec = nn.Linear(self.in_channels, self.embed_dim)
+        self._init_weights(self.proj_dec)
+
+    def forward(self, encoder_tokens: torch.Tensor, input_info: Dict):
+        H, W, N_H, N_W = self._grid(input_info)
+        x = self.adapt_tokens(encoder_tokens, input_info)
+        B, N, D = x.shape
+        assert N == N_H * N_W
+        s = int(self.preds_per_patch ** 0.5)
+        C = self.class_dim
+        if x.is_cuda and D % 64 == 0:
+            y = Fn.linear(_token_matrix(x), self.proj_dec.weight, self.proj_dec.bias, out_f32=True)
+        else:
+            y = F.linear(x.reshape(B * N, D).float(), self.proj_dec.weight, self.proj_dec.bias)
+        # 'b n (p c) -> b (n p) c' then 'b (nh nw ph pw) c -> b c (nh ph) (nw pw)', kept channels-last
+        y = y.reshape(B, N_H, N_W, s, s, C).permute(0, 1, 3, 2, 4, 5).reshape(B, N_H * s, N_W * s, C).contiguous()
+        for blk in self.blocks:
+            y = blk.forward_nhwc(y)
+        Hs, Ws = N_H * s, N_W * s
+        w = self.final_layer.weight.reshape(self.num_classes, C)
+        if y.is_cuda and C % 64 == 0:
+            y = Fn.linear_padded(Fn.to_bf16(y.reshape(B * Hs * Ws, C)), w, self.final_layer.bias)
+        else:
+            y = F.linear(y.reshape(B * Hs * Ws, C), w, self.final_layer.bias)
+        y = y.reshape(B, Hs, Ws, self.num_classes).permute(0, 3, 1, 2)
+        return F.interpolate(y, size=(H, W), mode=self.interpolate_mode)

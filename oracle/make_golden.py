@@ -14,6 +14,7 @@ Fixtures
   criterion.pt             MaskedMSELoss / MaskedCrossEntropyLoss incl. empty- and partial-mask cases
   cls.pt                   miragecls_factory['global'|'cls'|'token_mix'] logits + grads (ViT-B encoder)
   cls_large.pt             miragecls_factory['global'] logits + grads, ViT-L encoder (BASELINE configs[4])
+  seg.pt                   MIRAGELight + LinearSegAdapter / ConvNeXtAdapter predictions (seg-tuning caller)
 """
 from __future__ import annotations
 
@@ -249,9 +250,41 @@ def gen_cls(ref_wrap, ref_model, ref_in, size="base", pools=("global", "cls", "t
     torch.save({"weights_seed": 21, "input_seed": 9, "mask_seed": 13, "size": size, "out": out}, GOLDEN / fname)
 
 
+def gen_seg(ref_model, ref_in, ref_out):
+    """MIRAGELight (small encoder: dim 128, depth 2) with the two segmentation heads of the seg-tuning caller
+    (LinearSegAdapter, ConvNeXtAdapter; mirage/output_adapters.py:437-575), bscan 512x512, B = 2; also the
+    encoder's return_all_layers list (model.py:545-553)."""
+    a = argparse.Namespace()
+    a.in_domains = ["bscan"]
+    a.patch_size = {"bscan": (32, 32)}
+    a.input_size = {"bscan": (512, 512)}
+    a.grid_sizes = {"bscan": [16, 16]}
+    out = {}
+    for name, make in (("linear", lambda: ref_out.LinearSegAdapter(num_classes=13, main_tasks=("bscan",),
+                                                                    patch_size=[32, 32], task="bscan",
+                                                                    image_size=(512, 512))),
+                       ("convnext", lambda: ref_out.ConvNeXtAdapter(num_classes=13, embed_dim=2048, preds_per_patch=16,
+                                                                    main_tasks=("bscan",), patch_size=[32, 32],
+                                                                    depth=2, task="bscan", image_size=(512, 512)))):
+        with _quiet():
+            ins = {"bscan": ref_in.PatchedInputAdapter(num_channels=1, stride_level=1, patch_size_full=(32, 32),
+                                                       image_size=(512, 512))}
+            m = ref_model.MIRAGELight(a, input_adapters=ins, output_adapters={"bscan": make()},
+                                      num_global_tokens=1, dim_tokens=128, depth=2, num_heads=2,
+                                      drop_path_rate=0.0).eval()
+        load_synth_into(m, 31)
+        x = synth_images(2, ["bscan"], seed=41)
+        with torch.no_grad(), _quiet():
+            pred = m(dict(x))["bscan"]
+        out[name] = {"pred": subsample(pred, 128), "keys": sorted(m.state_dict().keys()),
+                     "n_params": sum(p.numel() for p in m.parameters())}
+        print("seg", name, tuple(pred.shape))
+    torch.save({"weights_seed": 31, "input_seed": 41, "batch": 2, "out": out}, GOLDEN / "seg.pt")
+
+
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    which = set(sys.argv[1:]) or {"encoder", "masks", "pretrain", "pretrain_large", "criterion", "cls", "cls_large"}
+    which = set(sys.argv[1:]) or {"encoder", "masks", "pretrain", "pretrain_large", "criterion", "cls", "cls_large", "seg"}
     ref_hf, ref_model, ref_in, ref_out, ref_crit, ref_wrap = import_reference()
     torch.set_num_threads(8)
     if "encoder" in which:
@@ -268,5 +301,7 @@ if __name__ == "__main__":
         gen_pretrain(ref_model, ref_in, ref_out, ref_crit, "large", 1024, 24, 16, 2, 8192)
     if "cls" in which:
         gen_cls(ref_wrap, ref_model, ref_in)
+    if "seg" in which:
+        gen_seg(ref_model, ref_in, ref_out)
     if "cls_large" in which:        # BASELINE configs[4] at its real model size (ViT-L), batch 2
         gen_cls(ref_wrap, ref_model, ref_in, size="large", pools=("global",), fname="cls_large.pt")

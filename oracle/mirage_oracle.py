@@ -440,3 +440,45 @@ def cls_state_dict_shapes(size: str, num_classes: int = 5, factor: int = 1) -> D
     sd["norm.weight"], sd["norm.bias"] = torch.ones(dim), torch.zeros(dim)
     sd["head.weight"], sd["head.bias"] = torch.zeros(num_classes, dim * factor), torch.zeros(num_classes)
     return sd
+
+
+# --------------------------------------------------------------------------------------------
+# segmentation heads of the MIRAGELight caller
+# --------------------------------------------------------------------------------------------
+def linear_seg_adapter(tokens: Tensor, sd: Dict[str, Tensor], pre: str, grid: Tuple[int, int],
+                       image_hw: Tuple[int, int], start: int = 0, mode: str = "bilinear") -> Tensor:
+    """LinearSegAdapter.forward, mirage/output_adapters.py:556-575: task tokens -> 'b (nh nw) d -> b d nh nw' ->
+    1x1 conv -> F.interpolate to the image size.  ``tokens`` [B, N_all + global, D]."""
+    nh, nw = grid
+    B, _, D = tokens.shape
+    x = tokens[:, start:start + nh * nw].reshape(B, nh, nw, D).permute(0, 3, 1, 2)           # :565-567
+    x = F.conv2d(x, sd[pre + "final_layer.weight"], sd[pre + "final_layer.bias"])            # :569
+    return F.interpolate(x, size=image_hw, mode=mode)                                        # :572
+
+
+def convnext_block(x: Tensor, sd: Dict[str, Tensor], pre: str) -> Tensor:
+    """ConvNeXtBlock.forward, mirage/output_adapter_utils.py:33-46 (gamma disabled, drop_path 0)."""
+    C = x.shape[1]
+    y = F.conv2d(x, sd[pre + "dwconv.weight"], sd[pre + "dwconv.bias"], padding=3, groups=C)  # :35
+    y = y.permute(0, 2, 3, 1)                                                                # :36
+    y = F.layer_norm(y, (C,), sd[pre + "norm.weight"], sd[pre + "norm.bias"], 1e-6)          # :37
+    y = F.gelu(y @ sd[pre + "pwconv1.weight"].t() + sd[pre + "pwconv1.bias"])                # :38-39
+    y = y @ sd[pre + "pwconv2.weight"].t() + sd[pre + "pwconv2.bias"]                        # :40
+    return x + y.permute(0, 3, 1, 2)                                                         # :43-45
+
+
+def convnext_adapter(tokens: Tensor, sd: Dict[str, Tensor], pre: str, grid: Tuple[int, int],
+                     image_hw: Tuple[int, int], preds_per_patch: int, depth: int, start: int = 0,
+                     mode: str = "bilinear") -> Tensor:
+    """ConvNeXtAdapter.forward, mirage/output_adapters.py:493-517."""
+    nh, nw = grid
+    B, _, D = tokens.shape
+    x = tokens[:, start:start + nh * nw] @ sd[pre + "proj_dec.weight"].t() + sd[pre + "proj_dec.bias"]   # :503
+    s = int(preds_per_patch ** 0.5)
+    C = x.shape[-1] // preds_per_patch
+    x = x.reshape(B, nh * nw * preds_per_patch, C)                                           # :504
+    x = x.reshape(B, nh, nw, s, s, C).permute(0, 5, 1, 3, 2, 4).reshape(B, C, nh * s, nw * s)  # :505-508
+    for i in range(depth):
+        x = convnext_block(x, sd, f"{pre}blocks.{i}.")                                       # :509
+    x = F.conv2d(x, sd[pre + "final_layer.weight"], sd[pre + "final_layer.bias"])            # :510
+    return F.interpolate(x, size=image_hw, mode=mode)                                        # :513

@@ -145,3 +145,54 @@ def test_cls_heads_golden():
         assert torch.allclose(logits, ref, rtol=2e-3, atol=2e-3), (pool, (logits - ref).abs().max())
         loss = torch.nn.functional.cross_entropy(logits, torch.tensor([1, 3])).item()
         assert abs(loss - g["out"][pool]["loss"]) <= 2e-3 * abs(g["out"][pool]["loss"])
+
+
+def test_seg_heads_golden():
+    """Oracle of the segmentation heads (mirage/output_adapters.py:437-575) against predictions recorded from the
+    reference's MIRAGELight + LinearSegAdapter / ConvNeXtAdapter; the product modules expose the same keys."""
+    from seg_case import build_seg_model, oracle_seg
+    g = torch.load(GOLDEN / "seg.pt")
+    x = synth_images(g["batch"], ["bscan"], seed=g["input_seed"])
+    for kind in ("linear", "convnext"):
+        m = build_seg_model(kind)
+        sd = m.state_dict()
+        assert sorted(sd.keys()) == g["out"][kind]["keys"]
+        assert sum(p.numel() for p in m.parameters()) == g["out"][kind]["n_params"]
+        sd.update(synth_state_dict({k: v.shape for k, v in sd.items()}, g["weights_seed"]))
+        with torch.no_grad():
+            pred = oracle_seg(x, sd, kind)
+        _check_sub(pred, g["out"][kind]["pred"], 5e-5)
+
+
+def test_checkpoint_schema_round_trip(tmp_path):
+    """mutils/checkpoint.py:9-72: save_model writes the reference's dictionary, auto_load_model resumes from the
+    newest numeric checkpoint and restores model / optimizer / epoch; the cls wrappers rebuild the model from the
+    pickled args of such a file (mirage_wrapper.py:59-62)."""
+    import argparse
+
+    from mirage_b200.checkpoint import auto_load_model, latest_checkpoint, save_model
+    from mirage_b200.optim import NativeScalerWithGradNormCount
+    from seg_case import build_seg_model
+    m = build_seg_model("linear")
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    for p in m.parameters():
+        if p.requires_grad:
+            p.grad = torch.randn_like(p)
+    opt.step()
+    args = argparse.Namespace(output_dir=str(tmp_path), auto_resume=True, resume="", model="miragelight_tiny")
+    scaler = NativeScalerWithGradNormCount()
+    for epoch in (3, 11):
+        path = save_model(args, epoch, m, opt, scaler)
+    assert latest_checkpoint(tmp_path).endswith("checkpoint-11.pth")
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"model", "optimizer", "epoch", "scaler", "args"} and ck["epoch"] == 11
+    assert ck["args"].model == "miragelight_tiny" and ck["scaler"] == {"scale": 1.0}
+    m2 = build_seg_model("linear")
+    opt2 = torch.optim.AdamW(m2.parameters(), lr=1e-3)
+    args2 = argparse.Namespace(output_dir=str(tmp_path), auto_resume=True, resume="")
+    auto_load_model(args2, m2, opt2, scaler)
+    assert args2.start_epoch == 12 and args2.resume.endswith("checkpoint-11.pth")
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    s1, s2 = opt.state_dict()["state"], opt2.state_dict()["state"]
+    assert s1.keys() == s2.keys() and all(torch.equal(s1[i]["exp_avg"], s2[i]["exp_avg"]) for i in s1)
