@@ -26,6 +26,11 @@
 //
 // The global-token remainder is peeled exactly as in attention.cu: the +1 KEY is a rank-1 update on CUDA cores
 // (score in the softmax thread, e * v_tail in the epilogue), the +1 QUERY row goes to attn_tail_rows4_kernel.
+// (Computing that row here with two spare warps reading the staged K / V blocks -- lane = key for the scores, lane =
+// output chunk for P V -- was implemented and measured twice in round 2: correct, but 0.63-0.65 ms vs 0.52 ms with
+// the separate kernel at cfg 2.  The two extra arrivals on every K / V stage-release barrier tie the TMA ring of
+// the four tiles to two latency-bound CUDA-core warps limited to 40 registers; round 1 saw the same in the
+// two-tile kernel.)
 #include "attention_common.cuh"
 
 namespace mb200 {
