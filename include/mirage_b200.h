@@ -170,13 +170,16 @@ int mb_layernorm_fwd(const float* x, const float* weight, const float* bias, voi
  * arriving through the residual branch); dx_bf16 (optional, contiguous bf16 [rows, dim]) receives the
  * same values rounded to bf16 -- the operand of the weight/data-gradient GEMMs that follow;
  * dweight/dbias f32 [dim], overwritten or accumulated.
+ * dx_colsum (optional, f32 [dim], overwritten or accumulated per dx_colsum_accumulate): column sums of dx = the
+ * bias gradient of the nn.Linear whose output gradient dx is (Attention.proj / Mlp.fc2, utils.py:157,186) --
+ * saves a separate mb_colsum pass over dx.
  * workspace: mb_layernorm_bwd_workspace(rows, dim) bytes of device memory. */
 int64_t mb_layernorm_bwd_workspace(int64_t rows, int64_t dim);
 int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* weight,
                      const float* mean, const float* rstd, const float* dres, float* dx,
                      void* dx_bf16, float* dweight, float* dbias, int32_t accumulate,
                      void* workspace, int64_t rows, int64_t dim, int64_t ldx, int64_t lddy,
-                     int64_t lddx, void* stream);
+                     int64_t lddx, float* dx_colsum, int32_t dx_colsum_accumulate, void* stream);
 
 /* out[c] (+)= sum_r a[r, c] -- bias gradient of every nn.Linear on the path. */
 int64_t mb_colsum_workspace(int64_t rows, int64_t cols);

@@ -120,7 +120,7 @@ _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES: dict[str, list] = {
     "mb_layernorm_fwd": [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp],
     "mb_layernorm_bwd": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
-                         _i64, _i64, _i64, _i64, _i64, _vp],
+                         _i64, _i64, _i64, _i64, _i64, _vp, _i32, _vp],
     "mb_colsum": [_vp, _i32, _vp, _i32, _vp, _i64, _i64, _i64, _vp],
     "mb_token_gather_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
     "mb_token_gather_bwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],

@@ -79,7 +79,10 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
 // dw = sum dy * xhat, db = sum dy partials in its own shared-memory slab (registers hold only the row
 // being processed, so two blocks fit per SM without spills).
 // Per-block partials go to part[blk, 2, D]; a second kernel reduces them (deterministic, no atomics).
-template <int VPL, bool DY_BF16>
+// DXSUM: a third per-warp slab accumulates the column sums of dx -- the bias gradient of the Linear layer whose
+// output gradient dx is (Attention.proj for the block's second LayerNorm, the previous block's Mlp.fc2 for the
+// first) -- so that no separate column-sum pass has to re-read dx.
+template <int VPL, bool DY_BF16, bool DXSUM>
 __global__ void __launch_bounds__(kRowThreads, 2)
 layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ w, const float* __restrict__ mean_in,
@@ -87,14 +90,16 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
                      float* __restrict__ part, long long M, int D, long long ldx, long long lddy,
                      long long lddx) {
-  extern __shared__ float sred[];  // [8 warps][2][D]
+  extern __shared__ float sred[];  // [8 warps][NS][D]
+  constexpr int NS = DXSUM ? 3 : 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* sw = sred + warp * 2 * D;
+  float* sw = sred + warp * NS * D;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int col = (i * 32 + lane) * 4;
     st4(sw + col, make_float4(0.f, 0.f, 0.f, 0.f));
     st4(sw + D + col, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (DXSUM) st4(sw + 2 * D + col, make_float4(0.f, 0.f, 0.f, 0.f));
   }
   const float invD = 1.f / D;
   for (long long row = (long long)blockIdx.x * (kRowThreads / 32) + warp; row < M;
@@ -145,6 +150,11 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       st4(dx + row * lddx + col, o);
+      if (DXSUM) {
+        float4 c = ld4(sw + 2 * D + col);
+        c.x += o.x; c.y += o.y; c.z += o.z; c.w += o.w;
+        st4(sw + 2 * D + col, c);
+      }
       if (dx_bf16) {
         uint2 pk;
         pk.x = pack_bf16x2(o.x, o.y);
@@ -155,11 +165,11 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
   }
   // block reduction of the parameter-gradient partials
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * D; c += kRowThreads) {
+  for (int c = threadIdx.x; c < NS * D; c += kRowThreads) {
     float acc = 0.f;
 #pragma unroll
-    for (int wv = 0; wv < kRowThreads / 32; ++wv) acc += sred[wv * 2 * D + c];
-    part[(long long)blockIdx.x * 2 * D + c] = acc;
+    for (int wv = 0; wv < kRowThreads / 32; ++wv) acc += sred[wv * NS * D + c];
+    part[(long long)blockIdx.x * NS * D + c] = acc;
   }
 }
 
@@ -169,7 +179,8 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
 // two outputs of D each (LayerNorm dweight | dbias).
 __global__ void __launch_bounds__(1024)
 colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1,
-                    int rows, int cols, int D, int accumulate) {
+                    int rows, int cols, int D, int accumulate, float* __restrict__ out2 = nullptr,
+                    int accumulate2 = 0) {
   __shared__ float sm[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
@@ -181,8 +192,13 @@ colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out0, fl
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < 32; ++k) t += sm[k][threadIdx.x];
-    float* o = (out1 == nullptr || c < D) ? (out0 + c) : (out1 + (c - D));
-    *o = accumulate ? (*o + t) : t;
+    if (out2 != nullptr && c >= 2 * D) {
+      float* o = out2 + (c - 2 * D);
+      *o = accumulate2 ? (*o + t) : t;
+    } else {
+      float* o = (out1 == nullptr || c < D) ? (out0 + c) : (out1 + (c - D));
+      *o = accumulate ? (*o + t) : t;
+    }
   }
 }
 
@@ -386,14 +402,14 @@ static int ln_bwd_blocks(int64_t rows) {
 }
 
 int64_t mb_layernorm_bwd_workspace(int64_t rows, int64_t dim) {
-  return (int64_t)ln_bwd_blocks(rows) * 2 * dim * (int64_t)sizeof(float);
+  return (int64_t)ln_bwd_blocks(rows) * 3 * dim * (int64_t)sizeof(float);
 }
 
 int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* weight,
                      const float* mean, const float* rstd, const float* dres, float* dx,
                      void* dx_bf16, float* dweight, float* dbias, int32_t accumulate,
                      void* workspace, int64_t rows, int64_t dim, int64_t ldx, int64_t lddy,
-                     int64_t lddx, void* stream) {
+                     int64_t lddx, float* dx_colsum, int32_t dx_colsum_accumulate, void* stream) {
   MB_REQUIRE(dy && x && weight && mean && rstd && dx && dweight && dbias && workspace,
              "mb_layernorm_bwd: null pointer");
   MB_REQUIRE(dim % 128 == 0 && dim >= 128 && dim <= 1024,
@@ -401,13 +417,16 @@ int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const flo
   MB_REQUIRE(rows > 0, "mb_layernorm_bwd: rows must be positive");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)ln_bwd_blocks(rows);
-  const size_t smem = (size_t)8 * 2 * dim * sizeof(float);
+  const int NS = dx_colsum != nullptr ? 3 : 2;
+  const size_t smem = (size_t)8 * NS * dim * sizeof(float);
   float* part = reinterpret_cast<float*>(workspace);
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   const int D = (int)dim;
 #define MB_LNB(V, BF)                                                                              \
+  if (NS == 3) MB_LNB_(V, BF, true) else MB_LNB_(V, BF, false)
+#define MB_LNB_(V, BF, DS)                                                                         \
   {                                                                                                \
-    auto kern = layernorm_bwd_kernel<V, BF>;                                                       \
+    auto kern = layernorm_bwd_kernel<V, BF, DS>;                                                   \
     if (smem > 48 * 1024)                                                                          \
       MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                          (int)smem));                                              \
@@ -424,9 +443,10 @@ int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const flo
   }
 #undef MB_LNB2
 #undef MB_LNB
+#undef MB_LNB_
   MB_CHECK_CUDA(cudaGetLastError());
-  colsum_final_kernel<<<(2 * D + 31) / 32, dim3(32, 32), 0, st>>>(part, dweight, dbias, (int)grid,
-                                                                   2 * D, D, accumulate);
+  colsum_final_kernel<<<(NS * D + 31) / 32, dim3(32, 32), 0, st>>>(part, dweight, dbias, (int)grid, NS * D, D,
+                                                                    accumulate, dx_colsum, dx_colsum_accumulate);
   MB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

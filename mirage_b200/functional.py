@@ -105,22 +105,32 @@ def grad_needed(*tensors) -> bool:
 # both, and the consumer (the next block's backward, or the GEMMs right after) asks for the bf16 view
 # through _as_bf16 without a cast kernel re-reading the fp32 tensor.  The fp32 tensor is kept alive
 # by the entry, so its storage cannot be recycled for a look-alike while the entry exists.
-_twin: dict = {"src": None, "ver": -1, "bf16": None}
+# The same kernel can also leave the COLUMN SUMS of that gradient (fp32 [D]): for the block below they are the
+# bias gradient of its Mlp.fc2, which would otherwise cost a column-sum pass over the whole tensor.
+_twin: dict = {"src": None, "ver": -1, "bf16": None, "colsum": None}
 
 
-def _remember_twin(src: torch.Tensor, bf16: torch.Tensor):
-    _twin["src"], _twin["ver"], _twin["bf16"] = src, src._version, bf16
+def _remember_twin(src: torch.Tensor, bf16: torch.Tensor, colsum: Optional[torch.Tensor] = None):
+    _twin["src"], _twin["ver"], _twin["bf16"], _twin["colsum"] = src, src._version, bf16, colsum
+
+
+def _take_twin(t: torch.Tensor):
+    """(bf16 twin, column sums or None) of ``t`` if it is the gradient the last LayerNorm backward produced."""
+    src = _twin["src"]
+    if (src is not None and t.dtype == torch.float32 and t.data_ptr() == src.data_ptr() and t.shape == src.shape
+            and t.stride() == src.stride() and t._version == _twin["ver"]):
+        out = (_twin["bf16"], _twin["colsum"])
+        _twin["src"] = _twin["bf16"] = _twin["colsum"] = None
+        return out
+    return None
 
 
 def _as_bf16(t: torch.Tensor) -> torch.Tensor:
     if t.dtype == torch.bfloat16:
         return t if t.stride(-1) == 1 else t.contiguous()
-    src = _twin["src"]
-    if (src is not None and t.data_ptr() == src.data_ptr() and t.shape == src.shape
-            and t.stride() == src.stride() and t._version == _twin["ver"]):
-        out = _twin["bf16"]
-        _twin["src"] = _twin["bf16"] = None
-        return out
+    hit = _take_twin(t)
+    if hit is not None:
+        return hit[0]
     return ops.cast_bf16(t.contiguous())
 
 
@@ -419,7 +429,8 @@ class _Block(Function):
         B, N, heads, hd = ctx.dims
         D = heads * hd
         dx2 = dx2.contiguous()
-        dyb = _as_bf16(dx2)
+        hit = _take_twin(dx2)          # produced by the block above: bf16 twin + column sums already there
+        dyb, dx2_colsum = hit if hit is not None else (_as_bf16(dx2), None)
         ps = (n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
         tg = [_sink_of(q) for q in ps]
         for wi, bi in ((0, 1), (6, 7)):
@@ -428,17 +439,24 @@ class _Block(Function):
                 tg[wi] = tg[bi] = None
         # MLP branch
         d_fc2_w = wgrad(dyb, g, into=tg[10])
-        d_fc2_b = ops.colsum(dyb, into=tg[11])
+        if dx2_colsum is None:
+            d_fc2_b = ops.colsum(dyb, into=tg[11])
+        elif tg[11] is not None:
+            d_fc2_b = tg[11].add_(dx2_colsum)
+        else:
+            d_fc2_b = dx2_colsum
         # fc1's bias gradient = column sums of dpre, accumulated by the dgrad epilogue that produces dpre
         d_fc1_b = tg[9] if tg[9] is not None else torch.zeros(fc1_w.shape[0], dtype=torch.float32, device=x.device)
         dpre = dgrad(dyb, bf16_weight(fc2_w), dgelu_aux=pre, colsum_out=d_fc1_b)
         d_fc1_w = wgrad(dpre, h2, into=tg[8])
         dh2 = dgrad(dpre, bf16_weight(fc1_w))
+        # the same pass leaves colsum(dx1) = Attention.proj's bias gradient
+        d_proj_b = tg[5] if tg[5] is not None else torch.empty(D, dtype=torch.float32, device=x.device)
         dx1, dx1b, d_n2w, d_n2b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2, want_bf16=True,
-                                                    dw_into=tg[6], db_into=tg[7])
+                                                    dw_into=tg[6], db_into=tg[7], dx_colsum=d_proj_b,
+                                                    dx_colsum_accumulate=tg[5] is not None)
         # attention branch
         d_proj_w = wgrad(dx1b, a, into=tg[4])
-        d_proj_b = ops.colsum(dx1b, into=tg[5])
         da = dgrad(dx1b, bf16_weight(proj_w))
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], a, da, lse,
@@ -447,9 +465,11 @@ class _Block(Function):
         d_qkv_w = wgrad(dqkv, h1, into=tg[2])
         d_qkv_b = ops.colsum(dqkv, into=tg[3])
         dh1 = dgrad(dqkv, bf16_weight(qkv_w))
+        # colsum(dx) is the fc2 bias gradient of the block BELOW (whose backward runs next and starts from dx)
+        dx_sum = torch.empty(D, dtype=torch.float32, device=x.device)
         dx, dxb, d_n1w, d_n1b = ops.layernorm_bwd(dh1, x, n1w, mean1, rstd1, dres=dx1, want_bf16=True,
-                                                  dw_into=tg[0], db_into=tg[1])
-        _remember_twin(dx, dxb)  # the previous block's backward starts by casting exactly this tensor
+                                                  dw_into=tg[0], db_into=tg[1], dx_colsum=dx_sum)
+        _remember_twin(dx, dxb, dx_sum)  # the previous block's backward starts by casting exactly this tensor
         grads = (d_n1w, d_n1b, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, d_n2w, d_n2b, d_fc1_w, d_fc1_b,
                  d_fc2_w, d_fc2_b)
         # completion is reported in the order the gradients were produced (output side first), which

@@ -186,9 +186,12 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: fl
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, mean: torch.Tensor,
                   rstd: torch.Tensor, dres: torch.Tensor | None = None, want_bf16: bool = False,
-                  dw_into: torch.Tensor | None = None, db_into: torch.Tensor | None = None):
+                  dw_into: torch.Tensor | None = None, db_into: torch.Tensor | None = None,
+                  dx_colsum: torch.Tensor | None = None, dx_colsum_accumulate: bool = False):
     """Returns (dx f32, dweight f32, dbias f32); dx includes dres when given.  With ``want_bf16`` the
-    kernel also writes dx rounded to bf16 and (dx, dx_bf16, dweight, dbias) is returned."""
+    kernel also writes dx rounded to bf16 and (dx, dx_bf16, dweight, dbias) is returned.
+    ``dx_colsum``: fp32 [dim] buffer that receives (or, with ``dx_colsum_accumulate``, accumulates) the column
+    sums of dx -- the bias gradient of the Linear whose output gradient dx is."""
     _req_cuda(dy, x, weight, mean, rstd, dres)
     rows, dim = x.shape
     dx = torch.empty((rows, dim), dtype=torch.float32, device=x.device)
@@ -205,6 +208,7 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, mean:
                                          x.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                          _ptr(dres), dx.data_ptr(), _ptr(dxb), dw.data_ptr(), db.data_ptr(), 1 if acc else 0,
                                          ws.data_ptr(), rows, dim, x.stride(0), dy.stride(0), dx.stride(0),
+                                         _ptr(dx_colsum), 1 if dx_colsum_accumulate else 0,
                                          _stream()), "mb_layernorm_bwd")
     if want_bf16:
         return dx, dxb, dw, db
