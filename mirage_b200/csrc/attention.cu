@@ -136,8 +136,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // work items.
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    if (warp == 0 && lane == 0) {
+    // (producer and issuers: whole converged warps, one elected lane around the TMA / MMA instructions -- see attention4.cu)
+    if (warp == 0) {
       // -------------------------------------------------------------- TMA producer
+      const bool leader = elect_one();
       int kv_count = 0, item_i = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i) {
         const int pair = item % p.q_pairs;
@@ -152,6 +154,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(&tail_free[slot], ph ^ 1);
           bytes += 2 * p.k_tail * 128;
         }
+        if (leader) {
         mbar_arrive_expect_tx(&q_full[slot], bytes);
         for (int g = 0; g < n_groups; ++g)
           tma_load_3d(smem + Cfg::kOffQ + (slot * 2 + g) * Cfg::kTileBytes, &tm_q, &q_full[slot], h * HD,
@@ -164,18 +167,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             bulk_load(tslot + (kMaxTail + t) * 128, p.v + row * p.ldv + h * HD, 128, &q_full[slot]);
           }
         }
+        }
+        __syncwarp();
         for (int j = 0; j < kvb; ++j, ++kv_count) {
           const int s = kv_count % kKvStages;
           const uint32_t kph = (kv_count / kKvStages) & 1;
           mbar_wait(&k_empty[s], kph ^ 1);
-          mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
-          tma_load_3d(smem + Cfg::kOffK + s * Cfg::kTileBytes, &tm_k, &k_full[s], h * HD, j * 128, b);
+          if (leader) {
+            mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
+            tma_load_3d(smem + Cfg::kOffK + s * Cfg::kTileBytes, &tm_k, &k_full[s], h * HD, j * 128, b);
+          }
           mbar_wait(&v_empty[s], kph ^ 1);
-          mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
-          tma_load_3d(smem + Cfg::kOffV + s * Cfg::kTileBytes, &tm_v, &v_full[s], h * HD, j * 128, b);
+          if (leader) {
+            mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
+            tma_load_3d(smem + Cfg::kOffV + s * Cfg::kTileBytes, &tm_v, &v_full[s], h * HD, j * 128, b);
+          }
+          __syncwarp();
         }
       }
-    } else if ((warp == 1 || warp == 2) && lane == 0) {
+    } else if (warp == 1 || warp == 2) {
       // -------------------------------------------------------------- MMA issuers
       // One issuing thread PER softmax group (warp 1 -> group 0, warp 2 -> group 1), each with blocking
       // waits in its own group's event order: S_g(j+1), then P_g V(j).  S runs one key block ahead of
@@ -184,7 +194,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // pulled both groups into lockstep, where they fight for the MUFU at the same time.
       // The shared K / V / Q slots are released by two commits (one per issuer; the issuer of group 0
       // commits twice for an item that has only one query tile).
-      const int g = warp - 1;
+      const int g = __shfl_sync(0xffffffffu, warp, 0) - 1;
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t q_addr = smem_u32(smem + Cfg::kOffQ);
       const uint32_t k_addr = smem_u32(smem + Cfg::kOffK);
       const uint32_t v_addr = smem_u32(smem + Cfg::kOffV);
@@ -201,18 +213,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t idesc_s = make_idesc(128, static_cast<uint32_t>((valid + 15) & ~15), kFmtBF16, 0, 0);
         const uint32_t qa = q_addr + ((item_i & 1) * 2 + g) * Cfg::kTileBytes;
         const uint32_t ka = k_addr + (kc % kKvStages) * Cfg::kTileBytes;
+        const uint64_t qd = make_smem_desc(qa, 0, kSbo, kSw), kd = make_smem_desc(ka, 0, kSbo, kSw);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_f16_ss(tmem_base + g * 128, make_smem_desc(qa + k * 32, 0, kSbo, kSw),
-                      make_smem_desc(ka + k * 32, 0, kSbo, kSw), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&s_full[g]);
-        ++sc;
-        umma_commit(&k_empty[kc % kKvStages]);
-        if (n_groups == 1) umma_commit(&k_empty[kc % kKvStages]);
-        if (j == kvb - 1) {  // last S of the item: its Q slot may go
-          umma_commit(&q_empty[item_i & 1]);
-          if (n_groups == 1) umma_commit(&q_empty[item_i & 1]);
+          for (int k = 0; k < HD / 16; ++k)   // +32 bytes per K step = +2 in the 16-byte address field
+            umma_f16_ss(tmem_u + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+          umma_commit(&k_empty[kc % kKvStages]);
+          if (n_groups == 1) umma_commit(&k_empty[kc % kKvStages]);
+          if (j == kvb - 1) {  // last S of the item: its Q slot may go
+            umma_commit(&q_empty[item_i & 1]);
+            if (n_groups == 1) umma_commit(&q_empty[item_i & 1]);
+          }
         }
+        __syncwarp();
+        ++sc;
       };
       auto issue_pv = [&](int n_groups, int j, int kc) {
         mbar_wait(&p_full[g], pc & 1);
@@ -222,14 +237,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int valid = min(128, p.Nk_main - j * 128);
         const int ksteps = (valid + 15) >> 4;
         const uint32_t va = v_addr + (kc % kKvStages) * Cfg::kTileBytes;
-        for (int kk = 0; kk < ksteps; ++kk)
-          umma_f16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + kk * 8,
-                      make_smem_desc(va + kk * 16 * Cfg::kRowBytes, 0, kSbo, kSw), idesc_pv,
-                      (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&o_full[g]);
+        const uint64_t vd = make_smem_desc(va, 0, kSbo, kSw);
+        if (leader) {
+          for (int kk = 0; kk < ksteps; ++kk)   // 16 keys = 16 rows of the V tile
+            umma_f16_ts(tmem_u + 256 + g * 64, tmem_u + 384 + g * 64 + kk * 8, vd + kk * (Cfg::kRowBytes),
+                        idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&o_full[g]);
+          umma_commit(&v_empty[kc % kKvStages]);
+          if (n_groups == 1) umma_commit(&v_empty[kc % kKvStages]);
+        }
+        __syncwarp();
         ++pc;
-        umma_commit(&v_empty[kc % kKvStages]);
-        if (n_groups == 1) umma_commit(&v_empty[kc % kKvStages]);
         if (j == kvb - 1) ++oc;
       };
 

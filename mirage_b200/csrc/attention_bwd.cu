@@ -124,29 +124,42 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    if (warp == 0 && lane == 0) {
+    // Producer and issuer run as whole, converged warps on warp-uniform values and elect one lane only around the
+    // TMA / MMA / commit instructions: under a `lane == 0` guard ptxas wraps every UTCHMMA / UTMALDG in an ELECT /
+    // R2UR.BROADCAST / BRA.U.ANY loop (~100 clk of serial issue each, see attention4.cu) -- with up to 32 MMAs per
+    // (key block, query tile) iteration against ~1300 clk of tensor work, issue WAS this kernel's critical path.
+    if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
+      const bool leader = elect_one();
       int t = 0, jb = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int h = item % p.H, b = item / p.H;
         for (int j = 0; j < kvb; ++j, ++jb) {
           const int ks = jb & 1;
           mbar_wait(&kv_empty[ks], ((jb >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&kv_full[ks], 2 * Cfg::kTileBytes);
-          tma_load_3d(smem + Cfg::kOffK + ks * Cfg::kTileBytes, &tm_k, &kv_full[ks], h * HD, j * 128, b);
-          tma_load_3d(smem + Cfg::kOffV + ks * Cfg::kTileBytes, &tm_v, &kv_full[ks], h * HD, j * 128, b);
+          if (leader) {
+            mbar_arrive_expect_tx(&kv_full[ks], 2 * Cfg::kTileBytes);
+            tma_load_3d(smem + Cfg::kOffK + ks * Cfg::kTileBytes, &tm_k, &kv_full[ks], h * HD, j * 128, b);
+            tma_load_3d(smem + Cfg::kOffV + ks * Cfg::kTileBytes, &tm_v, &kv_full[ks], h * HD, j * 128, b);
+          }
+          __syncwarp();
           for (int i = 0; i < qt; ++i, ++t) {
             const int qs = t & 1;
             mbar_wait(&qdo_empty[qs], ((t >> 1) & 1) ^ 1);
-            mbar_arrive_expect_tx(&qdo_full[qs], 3 * Cfg::kTileBytes);
-            tma_load_3d(smem + Cfg::kOffQ + qs * Cfg::kTileBytes, &tm_q, &qdo_full[qs], h * HD, i * 128, b);
-            tma_load_3d(smem + Cfg::kOffDO + qs * Cfg::kTileBytes, &tm_do, &qdo_full[qs], h * HD, i * 128, b);
-            tma_load_3d(smem + Cfg::kOffO + qs * Cfg::kTileBytes, &tm_o, &qdo_full[qs], h * HD, i * 128, b);
+            if (leader) {
+              mbar_arrive_expect_tx(&qdo_full[qs], 3 * Cfg::kTileBytes);
+              tma_load_3d(smem + Cfg::kOffQ + qs * Cfg::kTileBytes, &tm_q, &qdo_full[qs], h * HD, i * 128, b);
+              tma_load_3d(smem + Cfg::kOffDO + qs * Cfg::kTileBytes, &tm_do, &qdo_full[qs], h * HD, i * 128, b);
+              tma_load_3d(smem + Cfg::kOffO + qs * Cfg::kTileBytes, &tm_o, &qdo_full[qs], h * HD, i * 128, b);
+            }
+            __syncwarp();
           }
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t k_addr0 = smem_u32(smem + Cfg::kOffK);
       const uint32_t v_addr0 = smem_u32(smem + Cfg::kOffV);
       const uint32_t q_addr0 = smem_u32(smem + Cfg::kOffQ);
@@ -172,15 +185,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
         const uint32_t q_addr = q_addr0 + (t & 1) * Cfg::kTileBytes, do_addr = do_addr0 + (t & 1) * Cfg::kTileBytes;
         const uint32_t k_addr = k_addr0 + (jb & 1) * Cfg::kTileBytes, v_addr = v_addr0 + (jb & 1) * Cfg::kTileBytes;
+        // K step k = +32 bytes = +2 in the descriptor's 16-byte address field
+        const uint64_t qd = make_smem_desc(q_addr, 0, kSbo, kSw), kd = make_smem_desc(k_addr, 0, kSbo, kSw);
+        const uint64_t dod = make_smem_desc(do_addr, 0, kSbo, kSw), vd = make_smem_desc(v_addr, 0, kSbo, kSw);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_f16_ss(tmem_base + 0, make_smem_desc(q_addr + k * 32, 0, kSbo, kSw),
-                      make_smem_desc(k_addr + k * 32, 0, kSbo, kSw), idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_u + 0, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_f16_ss(tmem_base + 128, make_smem_desc(do_addr + k * 32, 0, kSbo, kSw),
-                      make_smem_desc(v_addr + k * 32, 0, kSbo, kSw), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(sdp_full);
+          for (int k = 0; k < HD / 16; ++k)
+            umma_f16_ss(tmem_u + 128, dod + 2 * k, vd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(sdp_full);
+        }
+        __syncwarp();
       };
 
       if (T > 0) mma1(0);
@@ -196,24 +212,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (t > 0) mbar_wait(acc_free, (t - 1) & 1);
         tc_fence_after();
         // dV_j += P^T dO_i ; dK_j += dS^T Q_i   (A = P / dS read MN-major: M = keys, K = query rows)
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16_ss(tmem_base + 256, make_smem_desc(p_addr + kk * 2048, 16384, 1024),
-                      make_smem_desc(do_addr + kk * kRowStep16, 0, kSbo, kSw), idesc_dkv,
-                      (i > 0 || kk > 0) ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16_ss(tmem_base + 320, make_smem_desc(ds_addr + kk * 2048, 16384, 1024),
-                      make_smem_desc(q_addr + kk * kRowStep16, 0, kSbo, kSw), idesc_dkv,
-                      (i > 0 || kk > 0) ? 1u : 0u);
-        // dQ_i(j) = dS K_j                      (A = dS K-major: M = query rows, K = keys)
+        // (descriptor address field in 16-byte units: +2048 bytes = +128, +kRowStep16 bytes = +kRowStep16 / 16)
+        const uint64_t pd = make_smem_desc(p_addr, 16384, 1024), dsd = make_smem_desc(ds_addr, 16384, 1024);
+        const uint64_t dsq = make_smem_desc(ds_addr, 0, 1024);
+        const uint64_t dod = make_smem_desc(do_addr, 0, kSbo, kSw), qd = make_smem_desc(q_addr, 0, kSbo, kSw);
+        const uint64_t kd = make_smem_desc(k_addr, 0, kSbo, kSw);
         const int ksteps = (valid + 15) >> 4;
-        for (int kk = 0; kk < ksteps; ++kk)
-          umma_f16_ss(tmem_base + 384, make_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
-                      make_smem_desc(k_addr + kk * kRowStep16, 0, kSbo, kSw), idesc_dq, kk > 0 ? 1u : 0u);
-        umma_commit(mma2_done);
-        umma_commit(&qdo_empty[t & 1]);
-        if (i == qt - 1) umma_commit(&kv_empty[jb & 1]);
+        if (leader) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16_ss(tmem_u + 256, pd + 128 * kk, dod + kk * (kRowStep16 >> 4), idesc_dkv,
+                        (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16_ss(tmem_u + 320, dsd + 128 * kk, qd + kk * (kRowStep16 >> 4), idesc_dkv,
+                        (i > 0 || kk > 0) ? 1u : 0u);
+          // dQ_i(j) = dS K_j                      (A = dS K-major: M = query rows, K = keys)
+          for (int kk = 0; kk < ksteps; ++kk)
+            umma_f16_ss(tmem_u + 384, dsq + (kk >> 2) * 1024 + (kk & 3) * 2, kd + kk * (kRowStep16 >> 4), idesc_dq,
+                        kk > 0 ? 1u : 0u);
+          umma_commit(mma2_done);
+          umma_commit(&qdo_empty[t & 1]);
+          if (i == qt - 1) umma_commit(&kv_empty[jb & 1]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp < 12) {
