@@ -39,6 +39,8 @@ class GemmArgs(C.Structure):
         ("up_gh", C.c_int32), ("up_gw", C.c_int32),
         ("cta_pair", C.c_int32),
         ("colsum_out", C.c_void_p),
+        ("twin_out", C.c_void_p), ("ld_twin", C.c_int64), ("row_stats", C.c_void_p),
+        ("ln_stats", C.c_void_p), ("ln_c1", C.c_void_p), ("ln_eps", C.c_float), ("pad_", C.c_int32),
     ]
 
 

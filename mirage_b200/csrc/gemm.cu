@@ -121,6 +121,12 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
   p.aux_in = reinterpret_cast<const __nv_bfloat16*>(a->aux_in);
   p.aux_out = reinterpret_cast<__nv_bfloat16*>(a->aux_out);
   p.colsum_out = a->colsum_out;
+  p.twin_out = reinterpret_cast<__nv_bfloat16*>(a->twin_out);
+  p.ld_twin = a->ld_twin;
+  p.row_stats = a->row_stats;
+  p.ln_stats = a->ln_stats;
+  p.ln_c1 = a->ln_c1;
+  p.ln_eps = a->ln_eps;
   p.M = (int)a->m;
   p.N = (int)a->n;
   p.K = (int)a->k;
@@ -181,6 +187,25 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
     }
   }
 
+  // folded LayerNorm (inference path): dedicated epilogues, plain K-major bf16 GEMMs only
+  const bool ln_any = a->twin_out != nullptr || a->ln_stats != nullptr;
+  if (ln_any) {
+    MB_REQUIRE(layout == LAY_KK_BF16 && !special && a->k_splits == 1 && !(a->epilogue & (MB_EPI_DGELU | MB_EPI_ATOMIC)),
+               "mb_gemm: the folded-LayerNorm epilogues need a plain K-major bf16 GEMM");
+    MB_REQUIRE(!(a->twin_out && a->ln_stats), "mb_gemm: twin_out and ln_stats are mutually exclusive");
+    if (a->twin_out) {
+      MB_REQUIRE(a->residual && p.out_f32 && a->row_stats && !(a->epilogue & MB_EPI_GELU) && a->ld_twin % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->twin_out) & 15) == 0,
+                 "mb_gemm: twin_out needs the f32 residual epilogue, row_stats and a 16-byte aligned twin");
+      epi = EPI_RES_LN;
+    } else {
+      MB_REQUIRE(a->ln_c1 && a->bias && !p.out_f32 && !a->residual && !a->aux_out &&
+                     (reinterpret_cast<uintptr_t>(a->ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(a->ln_c1) & 15) == 0,
+                 "mb_gemm: ln_stats needs ln_c1, bias, a bf16 output and no residual / aux_out");
+      epi = (a->epilogue & MB_EPI_GELU) ? EPI_GELU_LN : EPI_BF16_LN;
+    }
+  }
+
   CUtensorMap ta, tb;
   const TmaDtype tdt = tf32 ? kTmaF32 : kTmaBF16;
   // ---- A
@@ -227,6 +252,11 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
     if (make_tensor_map(&tb, a->b, tdt, 2, dims, str, box)) return -1;
   }
 
+  if (ln_any) {
+    const int rc_ln = dispatch_gemm_ln(bn, pair, epi, ta, tb, p, stream);
+    MB_REQUIRE(rc_ln != 1, "mb_gemm: no folded-LayerNorm kernel for block_n %d, pair %d", bn, (int)pair);
+    return rc_ln;
+  }
   int rc = pair ? dispatch_gemm_pair(bn, layout, epi, ta, tb, p, stream)
                 : dispatch_gemm_single(bn, layout, epi, ta, tb, p, stream);
   if (rc == 1 && epi != EPI_GENERIC)

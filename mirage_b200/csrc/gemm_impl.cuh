@@ -36,6 +36,13 @@ struct GemmDev {
   const __nv_bfloat16* aux_in;
   __nv_bfloat16* aux_out;
   float* colsum_out;  // EPI_DGELU: column sums of the output accumulate here (bias gradient)
+  // folded LayerNorm (see mb_gemm_args): producer side / consumer side
+  __nv_bfloat16* twin_out;
+  long long ld_twin;
+  float* row_stats;
+  const float* ln_stats;
+  const float* ln_c1;
+  float ln_eps;
   int M, N, K;
   long long ldc, ld_res, ld_aux;
   int res_period;
@@ -64,8 +71,14 @@ enum : int {
   EPI_MAP = 6,      // (+bias) (+fp32 residual, optionally periodic = pos-emb rows) -> fp32 through an
                     // output map (row map or un-patchify), index math hoisted out of the element loops:
                     // patch / semseg embedding into the token buffer, out_proj into image layout
-  EPI_COUNT = 7
+  EPI_RES_LN = 7,   // EPI_RES + bf16 twin of the output + per-row {sum, sum of squares} (atomics)   proj / fc2
+  EPI_BF16_LN = 8,  // LayerNorm folded in: rstd * acc - rstd * mean * c1[n] + c2[n] -> bf16               qkv
+  EPI_GELU_LN = 9,  // same, then GELU -> bf16                                                           fc1
+  EPI_COUNT = 10
 };
+
+constexpr bool epi_has_res(int mode) { return mode == EPI_RES || mode == EPI_RES_LN; }
+constexpr bool epi_ln_in(int mode) { return mode == EPI_BF16_LN || mode == EPI_GELU_LN; }
 
 constexpr int kGemmThreads = 384;
 constexpr int kBM = 128;
@@ -106,7 +119,8 @@ struct PairCfg {  // CTA pair per tile: each CTA holds BN/2 rows of B
 template <int MODE>
 struct EpiRegs {
   float4 bias;
-  float4 res[MODE == EPI_RES ? 8 : 1];
+  float4 c1;  // folded LayerNorm: column sums of gamma * W
+  float4 res[epi_has_res(MODE) ? 8 : 1];
   uint2 aux[MODE == EPI_DGELU ? 8 : 1];
 };
 
@@ -117,7 +131,11 @@ __device__ __forceinline__ void epi_prefetch(const GemmDev& p, EpiRegs<MODE>& r,
   const bool col_ok = col < p.N;
   if (p.bias != nullptr && first_split && col_ok)
     r.bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-  if constexpr (MODE == EPI_RES) {
+  if constexpr (epi_ln_in(MODE)) {
+    r.c1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_ok) r.c1 = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + col));
+  }
+  if constexpr (epi_has_res(MODE)) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int row = row_base + it * 4 + sub;
@@ -235,6 +253,28 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
     }
   }
 
+  // folded LayerNorm, consumer side: rstd and rstd * mean of this thread's 8 rows (statistics over K columns)
+  [[maybe_unused]] float ln_rstd[epi_ln_in(MODE) ? 8 : 1], ln_mr[epi_ln_in(MODE) ? 8 : 1];
+  if constexpr (epi_ln_in(MODE)) {
+    const float inv_k = 1.f / static_cast<float>(p.K);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row_base + it * 4 + sub;
+      float2 st = make_float2(0.f, 1.f);
+      if (row < p.M) st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + row);
+      const float mean = st.x * inv_k;
+      const float var = fmaxf(st.y * inv_k - mean * mean, 0.f);
+      ln_rstd[it] = rsqrtf(var + p.ln_eps);
+      ln_mr[it] = ln_rstd[it] * mean;
+    }
+  }
+  // producer side: row sums of this thread's 4-column chunks over all slabs of the tile
+  [[maybe_unused]] float rs1[MODE == EPI_RES_LN ? 8 : 1], rs2[MODE == EPI_RES_LN ? 8 : 1];
+  if constexpr (MODE == EPI_RES_LN) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) rs1[it] = rs2[it] = 0.f;
+  }
+
   mbar_wait(full_bar, full_parity);  // accumulator of this tile is complete
   tc_fence_after();
 
@@ -299,7 +339,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
       }
     } else {
       const long long row0 = row_base + sub;
-      constexpr int OUT_BYTES = (MODE == EPI_RES || MODE == EPI_F32) ? 4 : 2;
+      constexpr int OUT_BYTES = (epi_has_res(MODE) || MODE == EPI_F32) ? 4 : 2;
       uint8_t* optr = reinterpret_cast<uint8_t*>(p.out) + (row0 * p.ldc + col) * OUT_BYTES;
       const long long ostep = 4 * p.ldc * OUT_BYTES;
       __nv_bfloat16* aptr = nullptr;
@@ -315,9 +355,20 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int row = row_base + it * 4 + sub;
-        float f0 = acc[it].x + cur.bias.x, f1 = acc[it].y + cur.bias.y;
-        float f2 = acc[it].z + cur.bias.z, f3 = acc[it].w + cur.bias.w;
+        float f0, f1, f2, f3;
+        if constexpr (epi_ln_in(MODE)) {
+          f0 = fmaf(acc[it].x, ln_rstd[it], fmaf(-ln_mr[it], cur.c1.x, cur.bias.x));
+          f1 = fmaf(acc[it].y, ln_rstd[it], fmaf(-ln_mr[it], cur.c1.y, cur.bias.y));
+          f2 = fmaf(acc[it].z, ln_rstd[it], fmaf(-ln_mr[it], cur.c1.z, cur.bias.z));
+          f3 = fmaf(acc[it].w, ln_rstd[it], fmaf(-ln_mr[it], cur.c1.w, cur.bias.w));
+        } else {
+          f0 = acc[it].x + cur.bias.x; f1 = acc[it].y + cur.bias.y;
+          f2 = acc[it].z + cur.bias.z; f3 = acc[it].w + cur.bias.w;
+        }
         const bool ok = (row < p.M) && col_ok;
+        if constexpr (MODE == EPI_GELU_LN) {
+          gelu_fast2(f0, f1); gelu_fast2(f2, f3);
+        }
         if constexpr (MODE == EPI_GELU) {
           if (aptr != nullptr && ok) {
             uint2 pk;
@@ -334,8 +385,18 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
           f0 *= h0.x; f1 *= h0.y; f2 *= h1.x; f3 *= h1.y;
           if (ok) { cs0 += f0; cs1 += f1; cs2 += f2; cs3 += f3; }
         }
-        if constexpr (MODE == EPI_RES) {
+        if constexpr (epi_has_res(MODE)) {
           f0 += cur.res[it].x; f1 += cur.res[it].y; f2 += cur.res[it].z; f3 += cur.res[it].w;
+        }
+        if constexpr (MODE == EPI_RES_LN) {
+          if (ok) {
+            rs1[it] += (f0 + f1) + (f2 + f3);
+            rs2[it] += (f0 * f0 + f1 * f1) + (f2 * f2 + f3 * f3);
+            uint2 tw;
+            tw.x = pack_bf16x2(f0, f1);
+            tw.y = pack_bf16x2(f2, f3);
+            *reinterpret_cast<uint2*>(p.twin_out + static_cast<long long>(row) * p.ld_twin + col) = tw;
+          }
         }
         if (ok) {
           if constexpr (OUT_BYTES == 4) {
@@ -365,6 +426,22 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
       cur = nxt;
     }
     __syncwarp();  // the slab is rewritten by the next phase A
+  }
+  if constexpr (MODE == EPI_RES_LN) {
+    // the 8 lanes that share a row (j4 = 0..7) fold their partial sums; one reduction pair per row and warp
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        rs1[it] += __shfl_xor_sync(0xffffffffu, rs1[it], o);
+        rs2[it] += __shfl_xor_sync(0xffffffffu, rs2[it], o);
+      }
+      const int row = row_base + it * 4 + sub;
+      if (j4 == 0 && row < p.M) {
+        atomicAdd(p.row_stats + 2ll * row, rs1[it]);
+        atomicAdd(p.row_stats + 2ll * row + 1, rs2[it]);
+      }
+    }
   }
 }
 
@@ -788,5 +865,8 @@ int dispatch_gemm_single(int bn, int layout, int epi, const CUtensorMap& ta, con
                          const GemmDev& p, cudaStream_t stream);
 int dispatch_gemm_pair(int bn, int layout, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
                        const GemmDev& p, cudaStream_t stream);
+// folded-LayerNorm epilogues (EPI_RES_LN / EPI_BF16_LN / EPI_GELU_LN), K-major bf16 operands only (gemm_ln.cu)
+int dispatch_gemm_ln(int bn, bool pair, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p,
+                     cudaStream_t stream);
 
 }  // namespace mb200

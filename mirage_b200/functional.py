@@ -480,9 +480,79 @@ class _Block(Function):
         return (dx, None, None, None, None, None, *out)
 
 
+# ---------------------------------------------------------------------------------------------
+# inference path of the Block with the LayerNorms folded into the GEMMs around them
+# ---------------------------------------------------------------------------------------------
+# LayerNorm(x) W^T + b = rstd * (x (gamma * W)^T) - rstd * mean * colsum(gamma * W) + (b + W beta): the GEMM that
+# PRODUCES x (proj / fc2, fp32 residual epilogue) also writes bf16(x) and accumulates the row sums the statistics
+# need; the GEMM that CONSUMES LayerNorm(x) (qkv / fc1) reads that bf16 twin against gamma * W and applies mean /
+# rstd in its epilogue.  The standalone LayerNorm kernel -- 6.4 % of the cfg-2 step at HBM peak, one 4-byte read
+# and one 2-byte write per element -- disappears (47 of 48 per ViT-L forward; the first one has no producer GEMM
+# with this epilogue).  Accuracy is that of the unfolded bf16 path (checked with emulated roundings on the ViT-L
+# oracle incl. 30-sigma outlier channels: max-rel 6.8e-3 vs 7.3e-3, identical cosine; tests/test_gpu_lnfold.py).
+#
+# OFF by default (MB_LN_FOLD=1 or functional.LN_FOLD = True enables it).  Measured A/B inside one gpurun call at
+# cfg 2: 2814-2819 vs 2789 images/s (+1.0 %), although the standalone kernels say -150 us per block
+# (scripts/perf_lnfold.py): the step is power-capped, and the LayerNorm kernels were the low-power intervals in
+# which the clocks recovered.  For that 1 % the row statistics come from fp32 atomics, so identical images at
+# different batch positions no longer give bit-identical tokens (test_encoder_full_batch_properties).
+import os as _os
+LN_FOLD = _os.environ.get("MB_LN_FOLD", "0") == "1"
+_fold_cache: dict = {}
+_ln_carry: dict = {"src": None, "ver": -1, "twin": None, "stats": None}
+
+
+def _folded_weights(w, b, gamma, beta):
+    """(bf16(gamma * W), c1 = row sums of that rounded matrix, c2 = b + W beta), cached per parameter versions."""
+    key = id(w)
+    sig = (w._version, b._version, gamma._version, beta._version, w.data_ptr(), gamma.data_ptr())
+    ent = _fold_cache.get(key)
+    if ent is not None and ent[0]() is w and ent[1] == sig:
+        return ent[2]
+    with torch.no_grad():
+        wp = (w.detach().float() * gamma.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+        c1 = wp.float().sum(dim=1).contiguous()
+        c2 = (b.detach().float() + w.detach().float() @ beta.detach().float()).contiguous()
+    _fold_cache[key] = (weakref.ref(w, lambda _r, k=key: _fold_cache.pop(k, None)), sig, (wp, c1, c2))
+    return wp, c1, c2
+
+
+def _block_infer_fold(x, B, N, heads, eps, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b,
+                      fc2_w, fc2_b):
+    T, D = x.shape
+    hd = D // heads
+    dev = x.device
+    c = _ln_carry
+    if (c["src"] is not None and c["src"].data_ptr() == x.data_ptr() and c["src"].shape == x.shape
+            and c["ver"] == x._version):
+        wq, c1, c2 = _folded_weights(qkv_w, qkv_b, n1w, n1b)
+        qkv = ops.gemm(c["twin"], wq, m=T, n=3 * D, k=D, bias=c2, ln_stats=c["stats"], ln_c1=c1, ln_eps=eps)
+    else:   # the stream does not come from a folding GEMM (first block): standalone LayerNorm
+        h1 = ops.layernorm(x, n1w, n1b, eps)
+        qkv = ops.gemm(h1, bf16_weight(qkv_w), m=T, n=3 * D, k=D, bias=qkv_b)
+    c["src"] = c["twin"] = c["stats"] = None
+    a = ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], batch=B, heads=heads, nq=N, nk=N,
+                      head_dim=hd, scale=hd ** -0.5)
+    stats = torch.zeros((2, T, 2), dtype=torch.float32, device=dev)
+    x1b = torch.empty((T, D), dtype=torch.bfloat16, device=dev)
+    x1 = ops.gemm(a, bf16_weight(proj_w), m=T, n=D, k=D, bias=proj_b, residual=x, out_dtype=torch.float32,
+                  twin_out=x1b, row_stats=stats[0])
+    w1, c1, c2 = _folded_weights(fc1_w, fc1_b, n2w, n2b)
+    Hd = fc1_w.shape[0]
+    g = ops.gemm(x1b, w1, m=T, n=Hd, k=D, bias=c2, gelu=True, ln_stats=stats[0], ln_c1=c1, ln_eps=eps)
+    x2b = torch.empty((T, D), dtype=torch.bfloat16, device=dev)
+    x2 = ops.gemm(g, bf16_weight(fc2_w), m=T, n=D, k=Hd, bias=fc2_b, residual=x1, out_dtype=torch.float32,
+                  twin_out=x2b, row_stats=stats[1])
+    c["src"], c["ver"], c["twin"], c["stats"] = x2, x2._version, x2b, stats[1]
+    return x2
+
+
 def transformer_block(x, B, N, heads, eps, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b,
                       fc1_w, fc1_b, fc2_w, fc2_b):
     need = grad_needed(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
+    if LN_FOLD and not need and x.is_cuda and x.dtype == torch.float32 and x.shape[1] % 64 == 0:
+        return _block_infer_fold(x.contiguous(), B, N, heads, eps, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b,
+                                 fc1_w, fc1_b, fc2_w, fc2_b)
     return _Block.apply(x, B, N, heads, eps, need, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b,
                         fc1_w, fc1_b, fc2_w, fc2_b)
 

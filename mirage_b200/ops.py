@@ -76,7 +76,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int,
          img_hw: tuple[int, int] | None = None,
          out_row_map: tuple[int, int, int] | None = None,
          unpatch: tuple[int, int, int, int, int] | None = None, cta_pair: int = 0,
-         colsum_out: torch.Tensor | None = None) -> torch.Tensor:
+         colsum_out: torch.Tensor | None = None,
+         twin_out: torch.Tensor | None = None, row_stats: torch.Tensor | None = None,
+         ln_stats: torch.Tensor | None = None, ln_c1: torch.Tensor | None = None,
+         ln_eps: float = 1e-6) -> torch.Tensor:
     """out[m, n] = epilogue(A * B^T); see ``mb_gemm`` in include/mirage_b200.h for the contract.
 
     ``a`` / ``b`` are 2-D (or, for MB_A_PATCH32, the [B,1,H,W] fp32 image batch) with unit stride in
@@ -132,6 +135,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int,
     args.block_n = block_n
     args.cta_pair = cta_pair
     args.colsum_out = _ptr(colsum_out)
+    if twin_out is not None:      # producer of a folded LayerNorm: bf16 twin of the output + row statistics
+        assert row_stats is not None and twin_out.dtype == torch.bfloat16 and twin_out.stride(-1) == 1
+        assert row_stats.dtype == torch.float32 and row_stats.is_contiguous() and row_stats.shape == (m, 2)
+        args.twin_out, args.ld_twin, args.row_stats = twin_out.data_ptr(), twin_out.stride(0), row_stats.data_ptr()
+    if ln_stats is not None:      # consumer: LayerNorm applied in the epilogue
+        assert ln_c1 is not None and ln_stats.dtype == torch.float32 and ln_stats.is_contiguous()
+        assert ln_stats.shape == (m, 2) and ln_c1.dtype == torch.float32 and ln_c1.is_contiguous() and bias is not None
+        args.ln_stats, args.ln_c1, args.ln_eps = ln_stats.data_ptr(), ln_c1.data_ptr(), float(ln_eps)
     if out_row_map is not None:
         args.out_row_period, args.out_row_stride, args.out_row_offset = out_row_map
     if unpatch is not None:
