@@ -489,7 +489,7 @@ class _Block(Function):
 # rstd in its epilogue.  The standalone LayerNorm kernel -- 6.4 % of the cfg-2 step at HBM peak, one 4-byte read
 # and one 2-byte write per element -- disappears (47 of 48 per ViT-L forward; the first one has no producer GEMM
 # with this epilogue).  Accuracy is that of the unfolded bf16 path (checked with emulated roundings on the ViT-L
-# oracle incl. 30-sigma outlier channels: max-rel 6.8e-3 vs 7.3e-3, identical cosine; tests/test_gpu_lnfold.py).
+# fp32 restatement incl. 30-sigma outlier channels: max-rel 6.8e-3 vs 7.3e-3, identical cosine; tests/test_gpu_lnfold.py).
 #
 # OFF by default (MB_LN_FOLD=1 or functional.LN_FOLD = True enables it).  Measured A/B inside one gpurun call at
 # cfg 2: 2814-2819 vs 2789 images/s (+1.0 %), although the standalone kernels say -150 us per block
