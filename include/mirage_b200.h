@@ -34,6 +34,11 @@ int mb_sm_count(void);          /* SMs the persistent kernels size their grids t
  * that communication kernels running concurrently (the NCCL gradient all-reduce launched from inside backward)
  * find SMs without waiting for -- or delaying -- a whole compute wave.  Returns the previous value. */
 int mb_set_sm_reserve(int n);
+/* Programmatic dependent launch between this library's kernels (the prologue of kernel k+1 -- barrier init, TMEM
+ * allocation, descriptor prefetch -- overlaps the drain of kernel k; every such kernel executes
+ * griddepcontrol.wait before touching global memory, so results are unchanged).  Initial value: environment
+ * MB_PDL=1, else off.  Returns the previous setting. */
+int mb_set_pdl(int on);
 void mb_clear_tensor_map_cache(void);
 
 /* ---------------------------------------------------------------- GEMM --------------------- */

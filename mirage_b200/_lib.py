@@ -92,6 +92,8 @@ def _declare(lib):
     lib.mb_sm_count.restype = C.c_int
     lib.mb_set_sm_reserve.restype = C.c_int
     lib.mb_set_sm_reserve.argtypes = [C.c_int]
+    lib.mb_set_pdl.restype = C.c_int
+    lib.mb_set_pdl.argtypes = [C.c_int]
     lib.mb_clear_tensor_map_cache.restype = None
     lib.mb_gemm.restype = C.c_int
     lib.mb_gemm.argtypes = [C.POINTER(GemmArgs), vp]
@@ -152,7 +154,7 @@ SIGNATURES: dict[str, list] = {
 }
 
 # every symbol include/mirage_b200.h declares
-EXPORTED = ["mb_last_error", "mb_version", "mb_sm_count", "mb_set_sm_reserve", "mb_clear_tensor_map_cache", "mb_gemm",
+EXPORTED = ["mb_last_error", "mb_version", "mb_sm_count", "mb_set_sm_reserve", "mb_set_pdl", "mb_clear_tensor_map_cache", "mb_gemm",
             "mb_attn_fwd", "mb_attn_bwd", "mb_attn_bwd_workspace", "mb_layernorm_bwd_workspace",
             "mb_colsum_workspace", "mb_masked_loss_workspace", "mb_ln_meanpool_workspace", "mb_optim_blocks"]
 

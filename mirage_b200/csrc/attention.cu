@@ -129,6 +129,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
 
   auto groups_of = [&](int item) { return ((item % p.q_pairs) * 2 + 1 < p.q_tiles) ? 2 : 1; };
 
@@ -565,6 +566,7 @@ attn_tail_rows_kernel(const AttnDev p) {
   __shared__ float s_q[HD];
   __shared__ float s_red[8];
   __shared__ float s_o[4][HD];
+  pdl_sync();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
   const __nv_bfloat16* kbase = p.k + static_cast<long long>(b) * p.Nk * p.ldk + h * HD;
@@ -640,6 +642,7 @@ __global__ void __launch_bounds__(kTailThreads)
 attn_tail_rows4_kernel(const AttnDev p) {
   static_assert(HD == 64, "tail rows are only peeled for head_dim 64");
   extern __shared__ float tsm[];
+  pdl_sync();
   float* s_p = tsm;                        // [4][Nk_pad]
   const int nk_pad = (p.Nk + 3) & ~3;
   float* s_q = s_p + 4 * nk_pad;           // [4][64]   q * scale * log2(e)
@@ -807,8 +810,7 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
   const long long items = (long long)p.B * p.H * p.q_pairs;
   MB_REQUIRE(items > 0 && items < (1ll << 31), "mb_attn_fwd: %lld work items out of range", items);
   const long long grid = items < sm_count() ? items : sm_count();  // persistent CTAs
-  kern<<<(unsigned)grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_k(kern, dim3((unsigned)grid), dim3(kAttnThreads), Cfg::kSmemBytes, stream, tq, tk, tv, p));
   }
   if constexpr (HD == 64) {
     if (p.Nq_main < p.Nq) {
@@ -821,9 +823,10 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
           MB_CHECK_CUDA(cudaFuncSetAttribute(attn_tail_rows4_kernel<HD>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 + 16 * 1024));
         }
-        attn_tail_rows4_kernel<HD><<<(unsigned)(p.B * (p.H / 4)), kTailThreads, tsmem, stream>>>(p);
+        MB_CHECK_CUDA(launch_k(attn_tail_rows4_kernel<HD>, dim3((unsigned)(p.B * (p.H / 4))), dim3(kTailThreads), tsmem,
+                               stream, p));
       } else {
-        attn_tail_rows_kernel<HD><<<(unsigned)(p.B * p.H), kTailThreads, 0, stream>>>(p);
+        MB_CHECK_CUDA(launch_k(attn_tail_rows_kernel<HD>, dim3((unsigned)(p.B * p.H)), dim3(kTailThreads), 0, stream, p));
       }
     }
     MB_CHECK_CUDA(cudaGetLastError());

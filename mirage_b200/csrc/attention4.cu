@@ -183,6 +183,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
 
   if (warp < 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -555,8 +556,8 @@ static int launch4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
   const long long items = static_cast<long long>(p.B) * p.H * (p.q_tiles / kA4Groups);
   MB_REQUIRE(items > 0 && items < (1ll << 31), "mb_attn_fwd: %lld work items out of range", items);
   const long long grid = items < sm_count() ? items : sm_count();
-  kern<<<static_cast<unsigned>(grid), kA4Threads, A4Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_k(kern, dim3(static_cast<unsigned>(grid)), dim3(kA4Threads), A4Cfg::kSmemBytes, stream, tq, tk,
+                         tv, p));
   return 0;
 }
 

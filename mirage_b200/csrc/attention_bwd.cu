@@ -119,6 +119,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
   const int kvb = p.kv_blocks, qt = p.q_tiles;
   const int n_items = p.B * p.H;
 
@@ -481,8 +482,8 @@ static int launch_attn_bwd(const mb_attn_bwd_args* a, cudaStream_t stream) {
   }
   const long long items = (long long)p.B * p.H;
   const long long grid = items < sm_count() ? items : sm_count();  // persistent CTAs
-  kern<<<(unsigned)grid, kAttnBwdThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, tdo, to, p);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_k(kern, dim3((unsigned)grid), dim3(kAttnBwdThreads), Cfg::kSmemBytes, stream, tq, tk, tv, tdo,
+                         to, p));
   return 0;
 }
 

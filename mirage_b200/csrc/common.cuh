@@ -724,6 +724,40 @@ int make_tensor_map(CUtensorMap* out, const void* base, TmaDtype dtype, int rank
 // mb_set_sm_reserve() keeps free for concurrently running communication kernels (NCCL).
 int sm_count();
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched through launch_k() may start while its stream
+// predecessor is still draining: its CTAs become resident as SM resources free up and run their private
+// prologue (barrier init, TMEM allocation, descriptor prefetch, index math).  pdl_wait() blocks until the
+// predecessor grid has COMPLETED and its writes are visible -- nothing that reads or writes global memory may come
+// before it -- and pdl_trigger() lets this kernel's own successor start its prologue.  Both are no-ops for a
+// kernel launched without the attribute.  Only kernels that call pdl_wait() may be launched through launch_k()
+// (a kernel without the wait would simply run concurrently with its predecessor).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_trigger();
+}
+
+bool pdl_enabled();  // runtime.cu: mb_set_pdl() / environment MB_PDL
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // "do this once per device" (cudaFuncSetAttribute is a per-device setting): first() is true the first time
 // it is called with a given current device.
 struct PerDeviceOnce {

@@ -513,6 +513,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // everything above is private to the CTA; global memory is only touched below
 
   // The producer and the MMA issuer run as WHOLE, converged warps on warp-uniform values (loop counters, kernel
   // parameters, shuffled registers) and elect one lane only around the TMA / MMA / commit instructions themselves.
@@ -697,6 +698,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // everything above is private to the CTA; global memory is only touched below
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -835,8 +837,7 @@ int launch_gemm_single(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   }
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, p));
   return 0;
 }
 
@@ -852,8 +853,7 @@ int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev
   }
   const int max_clusters = sm_count() / 2;
   const int clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
-  kern<<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_k(kern, dim3(2 * clusters), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, p));
   return 0;
 }
 

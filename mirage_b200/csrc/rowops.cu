@@ -26,6 +26,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ b, void* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, long long M, int D, long long ldx, long long ldy,
                      float eps) {
+  pdl_sync();
   const long long row = (long long)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -102,6 +103,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
     if (DXSUM) st4(sw + 2 * D + col, make_float4(0.f, 0.f, 0.f, 0.f));
   }
   const float invD = 1.f / D;
+  pdl_sync();
   for (long long row = (long long)blockIdx.x * (kRowThreads / 32) + warp; row < M;
        row += (long long)gridDim.x * (kRowThreads / 32)) {
     const float mean = mean_in[row], rstd = rstd_in[row];
@@ -182,6 +184,7 @@ colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out0, fl
                     int rows, int cols, int D, int accumulate, float* __restrict__ out2 = nullptr,
                     int accumulate2 = 0) {
   __shared__ float sm[32][33];
+  pdl_sync();
   const int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
   if (c < cols)
@@ -214,6 +217,7 @@ colsum_partial_kernel(const void* __restrict__ a, float* __restrict__ part, floa
                       long long M, int N, long long lda, int rows_per_block, int cpb) {
   constexpr int EPC = IN_BF16 ? 8 : 4;  // elements per 16-byte chunk
   __shared__ float sm[256 * 8];
+  pdl_sync();
   const int lanes = 256 / cpb;
   const int cx = threadIdx.x % cpb, ly = threadIdx.x / cpb;
   const int chunk = blockIdx.y * cpb + cx;
@@ -346,6 +350,7 @@ __global__ void fill_rows_kernel(const float* __restrict__ glob, float* __restri
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                      long long n4) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = ld4(in + i * 4);
@@ -362,8 +367,8 @@ static int launch_ln_fwd(const float* x, const float* w, const float* b, void* y
   const unsigned grid = (unsigned)((M + 7) / 8);
 #define MB_LN(V)                                                                                   \
   case V:                                                                                          \
-    layernorm_fwd_kernel<V, OUT_BF16><<<grid, kRowThreads, 0, st>>>(x, w, b, y, mean, rstd, M, D,  \
-                                                                     ldx, ldy, eps);               \
+    MB_CHECK_CUDA(launch_k(layernorm_fwd_kernel<V, OUT_BF16>, dim3(grid), dim3(kRowThreads), 0, st, x, w, b, \
+                           y, mean, rstd, M, D, ldx, ldy, eps));                                   \
     break;
   switch (D / 128) {
     MB_LN(1) MB_LN(2) MB_LN(3) MB_LN(4) MB_LN(5) MB_LN(6) MB_LN(7) MB_LN(8)
@@ -430,8 +435,8 @@ int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const flo
     if (smem > 48 * 1024)                                                                          \
       MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                          (int)smem));                                              \
-    kern<<<grid, kRowThreads, smem, st>>>(dy, x, weight, mean, rstd, dres, dx, dxb, part, rows, D, \
-                                          ldx, lddy, lddx);                                        \
+    MB_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(kRowThreads), smem, st, dy, x, weight, mean,     \
+                           rstd, dres, dx, dxb, part, rows, D, ldx, lddy, lddx));                  \
   }
 #define MB_LNB2(V)                                                                                 \
   case V:                                                                                          \
@@ -445,9 +450,8 @@ int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const flo
 #undef MB_LNB
 #undef MB_LNB_
   MB_CHECK_CUDA(cudaGetLastError());
-  colsum_final_kernel<<<(NS * D + 31) / 32, dim3(32, 32), 0, st>>>(part, dweight, dbias, (int)grid, NS * D, D,
-                                                                    accumulate, dx_colsum, dx_colsum_accumulate);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_k(colsum_final_kernel, dim3((NS * D + 31) / 32), dim3(32, 32), 0, st, part, dweight, dbias,
+                         (int)grid, NS * D, D, accumulate, dx_colsum, dx_colsum_accumulate));
   return 0;
 }
 
@@ -493,14 +497,14 @@ int mb_colsum(const void* a, int32_t a_dtype, float* out, int32_t accumulate, vo
   // accumulate into a 16-byte aligned destination: single kernel with vector reductions
   float* direct = (accumulate && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? out : nullptr;
   if (a_dtype == MB_BF16)
-    colsum_partial_kernel<true><<<grid, 256, 0, st>>>(a, part, direct, rows, (int)cols, lda, rpb, cpb);
+    MB_CHECK_CUDA(launch_k(colsum_partial_kernel<true>, grid, dim3(256), 0, st, a, part, direct, rows, (int)cols, lda,
+                           rpb, cpb));
   else
-    colsum_partial_kernel<false><<<grid, 256, 0, st>>>(a, part, direct, rows, (int)cols, lda, rpb, cpb);
-  MB_CHECK_CUDA(cudaGetLastError());
+    MB_CHECK_CUDA(launch_k(colsum_partial_kernel<false>, grid, dim3(256), 0, st, a, part, direct, rows, (int)cols, lda,
+                           rpb, cpb));
   if (direct != nullptr) return 0;
-  colsum_final_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 32), 0, st>>>(
-      part, out, nullptr, gx, (int)cols, (int)cols, accumulate);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_k(colsum_final_kernel, dim3((unsigned)((cols + 31) / 32)), dim3(32, 32), 0, st, part, out,
+                         nullptr, gx, (int)cols, (int)cols, accumulate, nullptr, 0));
   return 0;
 }
 
@@ -560,10 +564,8 @@ int mb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
   MB_REQUIRE(n % 4 == 0, "mb_cast_f32_to_bf16: n must be a multiple of 4");
   if (n == 0) return 0;
   const long long n4 = n / 4;
-  cast_f32_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0,
-                         reinterpret_cast<cudaStream_t>(stream)>>>(
-      in, reinterpret_cast<__nv_bfloat16*>(out), n4);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_k(cast_f32_bf16_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0,
+                         reinterpret_cast<cudaStream_t>(stream), in, reinterpret_cast<__nv_bfloat16*>(out), n4));
   return 0;
 }
 

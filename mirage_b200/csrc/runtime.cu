@@ -4,6 +4,7 @@
 // descriptors (CUtensorMap) keyed by (pointer, dtype, dims, strides, box).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -43,6 +44,16 @@ int sm_count() {
   int n = sm_physical() - g_sm_reserve;
   n &= ~1;  // CTA pairs
   return n < 2 ? 2 : n;
+}
+
+static int g_pdl = -1;
+
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("MB_PDL");
+    g_pdl = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl != 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -162,6 +173,12 @@ int mb_sm_count(void) { return mb200::sm_count(); }
 int mb_set_sm_reserve(int n) {
   const int prev = mb200::g_sm_reserve;
   mb200::g_sm_reserve = n < 0 ? 0 : n;
+  return prev;
+}
+
+int mb_set_pdl(int on) {
+  const int prev = mb200::pdl_enabled() ? 1 : 0;
+  mb200::g_pdl = on ? 1 : 0;
   return prev;
 }
 
