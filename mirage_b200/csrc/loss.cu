@@ -6,7 +6,12 @@
 //   MaskedCrossEntropyLoss   mirage/criterion.py:31-51    (optional label smoothing)
 //
 //   per_b = sum_pix mask_up[b,pix] * e[b,pix] / sum_pix mask_up[b,pix]      e = mean_c (p-t)^2  |  CE
-//   loss  = nanmean_b(per_b)      (samples whose mask is empty are skipped; 0 if every mask is empty)
+//   loss  = nanmean_b(per_b)      (samples whose mask is empty or whose loss is NaN are skipped; 0 if every mask
+//                                  is empty; without a mask the plain mean, where a NaN propagates)
+// CE labels: -100 (torch's default ignore_index) gives zero loss and zero gradient but stays in the denominator,
+// as in the reference; any other label outside [0, C) makes the loss +inf (torch would raise a device assert).
+// One deviation: a NaN prediction under a ZERO mask pixel is skipped here, whereas the reference's `loss * mask`
+// turns it into NaN and drops the whole sample.
 //
 // Pass 1 writes per-(sample, chunk) partial sums (deterministic, no atomics); a one-block finalize
 // kernel produces the scalar loss and, for the backward pass, coef[b] = 1 / (masked_pixels_b *
@@ -95,6 +100,8 @@ mse_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
   }
 }
 
+constexpr long long kIgnoreIndex = -100;  // torch.nn.functional.cross_entropy default (criterion.py:33 passes none)
+
 // one thread per pixel; channel values are strided by H*W (coalesced across the warp per channel)
 __global__ void __launch_bounds__(kLossThreads)
 ce_partial_kernel(const float* __restrict__ logits, const long long* __restrict__ tgt,
@@ -111,8 +118,12 @@ ce_partial_kernel(const float* __restrict__ logits, const long long* __restrict_
     const float mk = mask_at(mask, b, h, w, scale, nw, n_tok);
     if (mk == 0.f) continue;
     const float* l = logits + (long long)b * C * hw + pix;
-    long long t = tgt[(long long)b * hw + pix];
-    t = t < 0 ? 0 : (t >= C ? C - 1 : t);
+    const long long t = tgt[(long long)b * hw + pix];
+    if (t == kIgnoreIndex) continue;  // F.cross_entropy's default ignore_index: zero loss, still in the denominator
+    if (t < 0 || t >= C) {            // torch raises a device assert; here the loss goes to +inf (visible, no sync)
+      acc = INFINITY;
+      continue;
+    }
     float mx = -INFINITY, se = 0.f, sl = 0.f, lt = 0.f;
     for (int c = 0; c < C; ++c) {
       const float v = l[(long long)c * hw];
@@ -149,8 +160,11 @@ ce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ tg
       for (int c = 0; c < C; ++c) d[(long long)c * hw] = 0.f;
       continue;
     }
-    long long t = tgt[(long long)b * hw + pix];
-    t = t < 0 ? 0 : (t >= C ? C - 1 : t);
+    const long long t = tgt[(long long)b * hw + pix];
+    if (t < 0 || t >= C) {  // ignore_index (and invalid labels, whose forward loss is already +inf): no gradient
+      for (int c = 0; c < C; ++c) d[(long long)c * hw] = 0.f;
+      continue;
+    }
     float mx = -INFINITY, se = 0.f;
     for (int c = 0; c < C; ++c) {
       const float v = l[(long long)c * hw];
@@ -192,13 +206,16 @@ __global__ void loss_finalize_kernel(const float* __restrict__ part, const long 
   if (threadIdx.x == 0) {
     int valid = 0;
     float tot = 0.f;
+    // masked form: nanmean over the per-sample means (criterion.py:49, :107) -- samples with an empty mask (0/0) or a
+    // NaN loss are skipped; unmasked form: plain mean, a NaN propagates ("we want it to stop training", :51)
+    auto counts = [&](int b) { return s_den[b] > 0.f && (mask == nullptr || s_num[b] == s_num[b]); };
     for (int b = 0; b < B; ++b)
-      if (s_den[b] > 0.f) {
+      if (counts(b)) {
         ++valid;
         tot += s_num[b] / s_den[b];
       }
     loss[0] = valid > 0 ? tot / valid : 0.f;
-    for (int b = 0; b < B; ++b) coef[b] = (s_den[b] > 0.f && valid > 0) ? 1.f / (s_den[b] * valid) : 0.f;
+    for (int b = 0; b < B; ++b) coef[b] = (counts(b) && valid > 0) ? 1.f / (s_den[b] * valid) : 0.f;
   }
 }
 

@@ -307,9 +307,13 @@ def masked_ce(logits: Tensor, target: Tensor, mask: Optional[Tensor], patch: int
               label_smoothing: float = 0.0) -> Tensor:
     """MaskedCrossEntropyLoss.forward, mirage/criterion.py:31-51."""
     logp = torch.log_softmax(logits, dim=1)
-    nll = -logp.gather(1, target.unsqueeze(1)).squeeze(1)
+    # F.cross_entropy(reduction='none') with its default ignore_index = -100: such pixels get zero loss (the
+    # smoothing term included) but are still counted by the mask sum below
+    keep = target != -100
+    nll = -logp.gather(1, target.clamp(min=0).unsqueeze(1)).squeeze(1)
     if label_smoothing > 0.0:
         nll = (1.0 - label_smoothing) * nll + label_smoothing * (-logp.mean(dim=1))
+    nll = torch.where(keep, nll, torch.zeros_like(nll))
     if mask is None:
         return nll.mean()
     if mask.sum() == 0:

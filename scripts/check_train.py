@@ -220,6 +220,47 @@ def group_loss():
                 ok &= report("   ce grad", lg.grad[live].flatten(0, 2), lr.grad[live].flatten(0, 2), tol=1e-4)
                 if name == "one_empty_sample":
                     ok &= bool((lg.grad[0] == 0).all())
+    # ignore_index (-100) pixels: zero loss / zero gradient, still in the denominator -- against the oracle AND
+    # against F.cross_entropy itself (the call the reference makes, criterion.py:33)
+    lab_ig = labels.clone()
+    lab_ig[torch.rand(lab_ig.shape, generator=g) < 0.2] = -100
+    m = masks["random"]
+    for crit, eps in ((ce, 0.0), (ce_ls, 0.1)):
+        lg = logits.to(dev).requires_grad_(True)
+        v = crit(lg, lab_ig.to(dev), mask=m.to(dev))
+        lr = logits.clone().requires_grad_(True)
+        vr = O.masked_ce(lr, lab_ig, m, 8, eps)
+        per_px = torch.nn.functional.cross_entropy(logits, lab_ig, reduction="none", label_smoothing=eps)
+        mu = m.view(B, 16, 16).repeat_interleave(8, 1).repeat_interleave(8, 2).float()
+        vt = ((per_px * mu).flatten(1).sum(1) / mu.flatten(1).sum(1)).nanmean()
+        good = abs(float(v.detach()) - float(vr.detach())) <= 1e-5 and abs(float(vr.detach()) - float(vt)) <= 1e-5
+        print(f"[{'PASS' if good else 'FAIL'}] masked_ce eps={eps} ignore_index: {float(v.detach()):.6f} vs "
+              f"{float(vr.detach()):.6f} (torch {float(vt):.6f})", flush=True)
+        ok &= good
+        v.backward()
+        vr.backward()
+        ok &= report("   ce grad (ignore_index)", lg.grad.flatten(0, 2), lr.grad.flatten(0, 2), tol=1e-4)
+        ok &= bool((lg.grad.permute(0, 2, 3, 1)[lab_ig.to(dev) == -100] == 0).all())
+    # a label outside [0, C) must not pass silently (torch raises a device assert): loss = +inf
+    bad = labels.clone()
+    bad[0, 0, 0] = 99
+    v = ce(logits.to(dev), bad.to(dev), mask=torch.ones(B, 256, dtype=torch.long, device=dev))
+    good = bool(torch.isinf(v))
+    print(f"[{'PASS' if good else 'FAIL'}] masked_ce out-of-range label -> {float(v)}", flush=True)
+    ok &= good
+    # a sample whose loss is NaN is skipped by the masked form's nanmean (criterion.py:49/:107)
+    pn = pred.clone()
+    pn[1, 0, 5, 5] = float("nan")
+    mo = torch.ones(B, 256, dtype=torch.long)
+    v = mse(pn.to(dev), tgt.to(dev), mask=mo.to(dev))
+    vr = O.masked_mse(pn, tgt, mo, 32)
+    good = abs(float(v) - float(vr)) <= 1e-5 and not bool(torch.isnan(v))
+    print(f"[{'PASS' if good else 'FAIL'}] masked_mse NaN sample skipped: {float(v):.6f} vs {float(vr):.6f}", flush=True)
+    ok &= good
+    v = mse(pn.to(dev), tgt.to(dev), mask=None)
+    good = bool(torch.isnan(v))
+    print(f"[{'PASS' if good else 'FAIL'}] masked_mse without mask propagates NaN: {float(v)}", flush=True)
+    ok &= good
     return ok
 
 
