@@ -36,9 +36,10 @@ int mb_sm_count(void);          /* SMs the persistent kernels size their grids t
 int mb_set_sm_reserve(int n);
 /* Programmatic dependent launch between this library's kernels (the prologue of kernel k+1 -- barrier init, TMEM
  * allocation, descriptor prefetch -- overlaps the drain of kernel k; every such kernel executes
- * griddepcontrol.wait before touching global memory, so results are unchanged).  Initial value: environment
- * MB_PDL=1, else off.  Returns the previous setting. */
-int mb_set_pdl(int on);
+ * griddepcontrol.wait before touching global memory, so results are unchanged).  `mode` is a bit mask: 1 = tensor
+ * kernels (GEMM, attention), 2 = row kernels (LayerNorm, column sums, casts, attention tail rows).  Initial value:
+ * environment MB_PDL (0..3), else 0.  Returns the previous setting. */
+int mb_set_pdl(int mode);
 void mb_clear_tensor_map_cache(void);
 
 /* ---------------------------------------------------------------- GEMM --------------------- */

@@ -129,7 +129,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();
+  pdl_wait();
 
   auto groups_of = [&](int item) { return ((item % p.q_pairs) * 2 + 1 < p.q_tiles) ? 2 : 1; };
 
@@ -186,6 +186,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           __syncwarp();
         }
       }
+      pdl_trigger();
     } else if (warp == 1 || warp == 2) {
       // -------------------------------------------------------------- MMA issuers
       // One issuing thread PER softmax group (warp 1 -> group 0, warp 2 -> group 1), each with blocking
@@ -823,10 +824,10 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
           MB_CHECK_CUDA(cudaFuncSetAttribute(attn_tail_rows4_kernel<HD>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 + 16 * 1024));
         }
-        MB_CHECK_CUDA(launch_k(attn_tail_rows4_kernel<HD>, dim3((unsigned)(p.B * (p.H / 4))), dim3(kTailThreads), tsmem,
+        MB_CHECK_CUDA(launch_row(attn_tail_rows4_kernel<HD>, dim3((unsigned)(p.B * (p.H / 4))), dim3(kTailThreads), tsmem,
                                stream, p));
       } else {
-        MB_CHECK_CUDA(launch_k(attn_tail_rows_kernel<HD>, dim3((unsigned)(p.B * p.H)), dim3(kTailThreads), 0, stream, p));
+        MB_CHECK_CUDA(launch_row(attn_tail_rows_kernel<HD>, dim3((unsigned)(p.B * p.H)), dim3(kTailThreads), 0, stream, p));
       }
     }
     MB_CHECK_CUDA(cudaGetLastError());

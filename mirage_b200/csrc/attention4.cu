@@ -183,7 +183,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();
+  pdl_wait();
 
   if (warp < 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -223,6 +223,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           tma_load_3d(smem + Cfg::kOffV + s * Cfg::kKvTile, &tm_v, &v_full[s], h * HD, j * kA4Block, b);
         }
       }
+      pdl_trigger();
     } else if (warp >= 1 && warp <= kA4Groups) {
       // -------------------------------------------------------------- MMA issuer of query tile g
       // Event order of one tile: S(0) | P(0) -> PV(0), S(1) | P(1) -> PV(1), S(2) | ...  S_g and P_g alias in

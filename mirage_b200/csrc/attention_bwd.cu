@@ -119,7 +119,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();
+  pdl_wait();
   const int kvb = p.kv_blocks, qt = p.q_tiles;
   const int n_items = p.B * p.H;
 
@@ -157,6 +157,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
       }
+      pdl_trigger();
     } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer
       const bool leader = elect_one();

@@ -740,9 +740,12 @@ __device__ __forceinline__ void pdl_sync() {
   pdl_trigger();
 }
 
-bool pdl_enabled();  // runtime.cu: mb_set_pdl() / environment MB_PDL
+// Kernel classes for the switch: tensor kernels (GEMM, attention: trigger once their last operand tile is
+// requested) and row kernels (LayerNorm, column sums, casts: trigger right after their own wait).
+enum : int { kPdlTensor = 1, kPdlRow = 2 };
+int pdl_mode();  // runtime.cu: mb_set_pdl() / environment MB_PDL, bit mask of the classes above
 
-template <typename... KArgs, typename... Args>
+template <int CLS = kPdlTensor, typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                             Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -754,8 +757,13 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_mode() & CLS) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_row(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  return launch_k<kPdlRow>(kern, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 
 // "do this once per device" (cudaFuncSetAttribute is a per-device setting): first() is true the first time

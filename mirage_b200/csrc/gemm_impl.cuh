@@ -513,7 +513,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();  // everything above is private to the CTA; global memory is only touched below
+  pdl_wait();  // everything above is private to the CTA; global memory is only touched below
 
   // The producer and the MMA issuer run as WHOLE, converged warps on warp-uniform values (loop counters, kernel
   // parameters, shuffled registers) and elect one lane only around the TMA / MMA / commit instructions themselves.
@@ -563,6 +563,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       }
     }
+    pdl_trigger();  // last operand tile requested: the successor may start its prologue while this CTA drains
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     const bool leader = elect_one();
@@ -698,7 +699,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();  // everything above is private to the CTA; global memory is only touched below
+  pdl_wait();  // everything above is private to the CTA; global memory is only touched below
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -744,6 +745,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
     }
+    pdl_trigger();
   } else if (warp == 1 && cta == 0) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     const bool leader = elect_one();

@@ -367,7 +367,7 @@ static int launch_ln_fwd(const float* x, const float* w, const float* b, void* y
   const unsigned grid = (unsigned)((M + 7) / 8);
 #define MB_LN(V)                                                                                   \
   case V:                                                                                          \
-    MB_CHECK_CUDA(launch_k(layernorm_fwd_kernel<V, OUT_BF16>, dim3(grid), dim3(kRowThreads), 0, st, x, w, b, \
+    MB_CHECK_CUDA(launch_row(layernorm_fwd_kernel<V, OUT_BF16>, dim3(grid), dim3(kRowThreads), 0, st, x, w, b, \
                            y, mean, rstd, M, D, ldx, ldy, eps));                                   \
     break;
   switch (D / 128) {
@@ -435,7 +435,7 @@ int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const flo
     if (smem > 48 * 1024)                                                                          \
       MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                          (int)smem));                                              \
-    MB_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(kRowThreads), smem, st, dy, x, weight, mean,     \
+    MB_CHECK_CUDA(launch_row(kern, dim3(grid), dim3(kRowThreads), smem, st, dy, x, weight, mean,     \
                            rstd, dres, dx, dxb, part, rows, D, ldx, lddy, lddx));                  \
   }
 #define MB_LNB2(V)                                                                                 \
@@ -450,7 +450,7 @@ int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const flo
 #undef MB_LNB
 #undef MB_LNB_
   MB_CHECK_CUDA(cudaGetLastError());
-  MB_CHECK_CUDA(launch_k(colsum_final_kernel, dim3((NS * D + 31) / 32), dim3(32, 32), 0, st, part, dweight, dbias,
+  MB_CHECK_CUDA(launch_row(colsum_final_kernel, dim3((NS * D + 31) / 32), dim3(32, 32), 0, st, part, dweight, dbias,
                          (int)grid, NS * D, D, accumulate, dx_colsum, dx_colsum_accumulate));
   return 0;
 }
@@ -497,13 +497,13 @@ int mb_colsum(const void* a, int32_t a_dtype, float* out, int32_t accumulate, vo
   // accumulate into a 16-byte aligned destination: single kernel with vector reductions
   float* direct = (accumulate && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? out : nullptr;
   if (a_dtype == MB_BF16)
-    MB_CHECK_CUDA(launch_k(colsum_partial_kernel<true>, grid, dim3(256), 0, st, a, part, direct, rows, (int)cols, lda,
+    MB_CHECK_CUDA(launch_row(colsum_partial_kernel<true>, grid, dim3(256), 0, st, a, part, direct, rows, (int)cols, lda,
                            rpb, cpb));
   else
-    MB_CHECK_CUDA(launch_k(colsum_partial_kernel<false>, grid, dim3(256), 0, st, a, part, direct, rows, (int)cols, lda,
+    MB_CHECK_CUDA(launch_row(colsum_partial_kernel<false>, grid, dim3(256), 0, st, a, part, direct, rows, (int)cols, lda,
                            rpb, cpb));
   if (direct != nullptr) return 0;
-  MB_CHECK_CUDA(launch_k(colsum_final_kernel, dim3((unsigned)((cols + 31) / 32)), dim3(32, 32), 0, st, part, out,
+  MB_CHECK_CUDA(launch_row(colsum_final_kernel, dim3((unsigned)((cols + 31) / 32)), dim3(32, 32), 0, st, part, out,
                          nullptr, gx, (int)cols, (int)cols, accumulate, nullptr, 0));
   return 0;
 }
@@ -564,7 +564,7 @@ int mb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
   MB_REQUIRE(n % 4 == 0, "mb_cast_f32_to_bf16: n must be a multiple of 4");
   if (n == 0) return 0;
   const long long n4 = n / 4;
-  MB_CHECK_CUDA(launch_k(cast_f32_bf16_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0,
+  MB_CHECK_CUDA(launch_row(cast_f32_bf16_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0,
                          reinterpret_cast<cudaStream_t>(stream), in, reinterpret_cast<__nv_bfloat16*>(out), n4));
   return 0;
 }

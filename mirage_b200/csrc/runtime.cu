@@ -48,12 +48,12 @@ int sm_count() {
 
 static int g_pdl = -1;
 
-bool pdl_enabled() {
+int pdl_mode() {
   if (g_pdl < 0) {
     const char* e = getenv("MB_PDL");
-    g_pdl = (e != nullptr && e[0] == '1') ? 1 : 0;
+    g_pdl = (e != nullptr && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
   }
-  return g_pdl != 0;
+  return g_pdl;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -177,8 +177,8 @@ int mb_set_sm_reserve(int n) {
 }
 
 int mb_set_pdl(int on) {
-  const int prev = mb200::pdl_enabled() ? 1 : 0;
-  mb200::g_pdl = on ? 1 : 0;
+  const int prev = mb200::pdl_mode();
+  mb200::g_pdl = on & 3;
   return prev;
 }
 
