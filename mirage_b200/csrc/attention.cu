@@ -767,6 +767,19 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
   }
   bool main_done = false;
   if constexpr (HD == 64) {
+    // one query tile x one key tile (the 99-token sequences of a pretraining step): attention_small.cu;
+    // MB_ATTN_SMALL=0 disables it
+    static int use_small = -1;
+    if (use_small < 0) {
+      const char* e = getenv("MB_ATTN_SMALL");
+      use_small = e ? atoi(e) : 1;
+    }
+    if (use_small && p.Nq <= 128 && p.Nk <= 128) {
+      const int rc = launch_attn_fwd_small(a, p, stream);
+      if (rc <= 0) return rc;
+    }
+  }
+  if constexpr (HD == 64) {
     // long sequences in whole quads of query tiles: the four-tile kernel (attention4.cu); MB_ATTN_V4=0 disables it
     static int use_v4 = -1;
     if (use_v4 < 0) {

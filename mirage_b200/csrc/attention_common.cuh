@@ -175,5 +175,7 @@ __device__ __forceinline__ float exp_row(uint32_t (&sreg)[64], float scale_log2,
 
 // launcher of the four-tile kernel (attention4.cu); returns 1 when the problem does not fit its assumptions
 int launch_attn_fwd4(const mb_attn_args* a, const AttnDev& p, int poly, cudaStream_t stream);
+// launcher of the single-tile kernel (attention_small.cu: head_dim 64, Nq <= 128, Nk <= 128); same convention
+int launch_attn_fwd_small(const mb_attn_args* a, const AttnDev& p, cudaStream_t stream);
 
 }  // namespace mb200

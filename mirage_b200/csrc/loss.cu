@@ -188,19 +188,25 @@ __global__ void loss_finalize_kernel(const float* __restrict__ part, const long 
   extern __shared__ float s_per[];  // [B] numerators, then [B] denominators
   float* s_num = s_per;
   float* s_den = s_per + B;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+  // one warp per sample: lanes stride over the chunk partials and the mask tokens (coalesced), fixed-order
+  // shuffle reduction -> deterministic
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int b = warp; b < B; b += nwarps) {
     float n = 0.f;
-    for (int c = 0; c < chunks; ++c) n += part[(long long)b * chunks + c];
+    for (int c = lane; c < chunks; c += 32) n += part[(long long)b * chunks + c];
+    n = warp_sum(n);
     float d;
     if (mask == nullptr) {
       d = (float)pixels;
     } else {
-      long long cnt = 0;
-      for (int t = 0; t < n_tok; ++t) cnt += mask[(long long)b * n_tok + t];
-      d = (float)cnt * scale * scale;
+      float cnt = 0.f;  // token counts are far below 2^24: exact in fp32
+      for (int t = lane; t < n_tok; t += 32) cnt += (float)mask[(long long)b * n_tok + t];
+      d = warp_sum(cnt) * scale * scale;
     }
-    s_num[b] = n;
-    s_den[b] = d;
+    if (lane == 0) {
+      s_num[b] = n;
+      s_den[b] = d;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -249,7 +255,7 @@ int mb_masked_mse_fwd(const float* pred, const float* target, const int64_t* mas
       pred, target, reinterpret_cast<const long long*>(mask), part, (int)channels, (int)height,
       (int)width, scale);
   MB_CHECK_CUDA(cudaGetLastError());
-  loss_finalize_kernel<<<1, 256, 2 * batch * sizeof(float), st>>>(
+  loss_finalize_kernel<<<1, 1024, 2 * batch * sizeof(float), st>>>(
       part, reinterpret_cast<const long long*>(mask), loss, coef, (int)batch, chunks,
       (int)((height / scale) * (width / scale)), scale, height * width);
   MB_CHECK_CUDA(cudaGetLastError());
@@ -284,7 +290,7 @@ int mb_masked_ce_fwd(const float* logits, const int64_t* target, const int64_t* 
       logits, reinterpret_cast<const long long*>(target), reinterpret_cast<const long long*>(mask),
       part, (int)channels, (int)height, (int)width, scale, label_smoothing);
   MB_CHECK_CUDA(cudaGetLastError());
-  loss_finalize_kernel<<<1, 256, 2 * batch * sizeof(float), st>>>(
+  loss_finalize_kernel<<<1, 1024, 2 * batch * sizeof(float), st>>>(
       part, reinterpret_cast<const long long*>(mask), loss, coef, (int)batch, chunks,
       (int)((height / scale) * (width / scale)), scale, height * width);
   MB_CHECK_CUDA(cudaGetLastError());

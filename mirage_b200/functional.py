@@ -210,6 +210,20 @@ def dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, *, out_dtype=torch.bfloat16, d
                     dgelu_aux=dgelu_aux, colsum_out=colsum_out)
 
 
+def _wb_grads(weight, bias, dyb, x, need_w=True, need_b=True):
+    """(dW, db) of y = x W^T + b as the autograd node should return them: with a gradient sink set, the wgrad GEMM
+    and the column-sum kernel accumulate straight into the parameter's bucket view and None is returned (no
+    temporary, no AccumulateGrad add kernel); otherwise fresh tensors."""
+    dw = db = None
+    if need_w:
+        tw = _sink_of(weight)
+        dw = _done(weight, tw, wgrad(dyb, x, into=tw))
+    if bias is not None and need_b:
+        tb = _sink_of(bias)
+        db = _done(bias, tb, ops.colsum(dyb, into=tb))
+    return dw, db
+
+
 # ---------------------------------------------------------------------------------------------
 # Linear
 # ---------------------------------------------------------------------------------------------
@@ -224,18 +238,16 @@ class _Linear(Function):
         y = ops.gemm(x, wb, m=T, n=N, k=K, bias=bias, residual=residual,
                      out_dtype=torch.float32 if (out_f32 or residual is not None) else torch.bfloat16)
         if save:
-            ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
+            ctx.save_for_backward(x, weight, bias)
         ctx.has_res = residual is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, weight, bias = ctx.saved_tensors
         dyb = _as_bf16(dy)
         dx = dgrad(dyb, bf16_weight(weight)) if ctx.needs_input_grad[0] else None
-        dw = wgrad(dyb, x) if ctx.needs_input_grad[1] else None
-        db = ops.colsum(dyb) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dw, db = _wb_grads(weight, bias, dyb, x, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
         return dx, dw, db, dres, None, None
 
@@ -267,16 +279,19 @@ class _LayerNorm(Function):
         if save:
             y, mean, rstd = ops.layernorm(x, weight, bias, eps, save_stats=True,
                                           out_dtype=torch.float32 if out_f32 else torch.bfloat16)
-            ctx.save_for_backward(x, weight, mean, rstd)
+            ctx.save_for_backward(x, weight, bias, mean, rstd)
         else:
             y = ops.layernorm(x, weight, bias, eps, out_dtype=torch.float32 if out_f32 else torch.bfloat16)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, mean, rstd = ctx.saved_tensors
-        dx, dw, db = ops.layernorm_bwd(dy.contiguous(), x, weight, mean, rstd)
-        return dx, dw, db, None, None, None
+        x, weight, bias, mean, rstd = ctx.saved_tensors
+        tw, tb = _sink_of(weight), _sink_of(bias)
+        if tw is None or tb is None:                  # the kernel accumulates both or neither
+            tw = tb = None
+        dx, dw, db = ops.layernorm_bwd(dy.contiguous(), x, weight, mean, rstd, dw_into=tw, db_into=tb)
+        return dx, _done(weight, tw, dw), _done(bias, tb, db), None, None, None
 
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6,
@@ -363,19 +378,17 @@ class _Mlp(Function):
         y = ops.gemm(g, bf16_weight(w2), m=T, n=w2.shape[0], k=Hd, bias=b2, residual=residual,
                      out_dtype=torch.float32 if residual is not None else torch.bfloat16)
         if need:
-            ctx.save_for_backward(x, w1, w2, pre, g)
+            ctx.save_for_backward(x, w1, b1, w2, b2, pre, g)
             ctx.has_res = residual is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w1, w2, pre, g = ctx.saved_tensors
+        x, w1, b1, w2, b2, pre, g = ctx.saved_tensors
         dyb = _as_bf16(dy)
-        dw2 = wgrad(dyb, g)
-        db2 = ops.colsum(dyb)
+        dw2, db2 = _wb_grads(w2, b2, dyb, g)
         dpre = dgrad(dyb, bf16_weight(w2), dgelu_aux=pre)      # (dy W2) * gelu'(pre), bf16 [T, Hd]
-        dw1 = wgrad(dpre, x)
-        db1 = ops.colsum(dpre)
+        dw1, db1 = _wb_grads(w1, b1, dpre, x)
         dx = dgrad(dpre, bf16_weight(w1)) if ctx.needs_input_grad[0] else None
         dres = dy if ctx.has_res else None
         return dx, dw1, db1, dw2, db2, dres, None
@@ -716,17 +729,18 @@ class _ProjUnpatch(Function):
         img = ops.gemm(x, bf16_weight(weight), m=T, n=weight.shape[0], k=K, bias=bias,
                        out_dtype=torch.float32, unpatch=geom)
         if save:
-            ctx.save_for_backward(x, weight)
+            ctx.save_for_backward(x, weight, bias)
             ctx.geom = geom
         return img
 
     @staticmethod
     def backward(ctx, dimg):
-        x, weight = ctx.saved_tensors
+        x, weight, bias = ctx.saved_tensors
         C_, ph, pw, gh, gw = ctx.geom
         dyb = ops.patchify_cast(dimg.contiguous().float(), ph, pw)          # [T, C*ph*pw] bf16
         dx = dgrad(dyb, bf16_weight(weight)) if ctx.needs_input_grad[0] else None
-        return dx, wgrad(dyb, x), ops.colsum(dyb), None, None
+        dw, db = _wb_grads(weight, bias, dyb, x)
+        return dx, dw, db, None, None
 
 
 def proj_unpatch(x, weight, bias, geom):

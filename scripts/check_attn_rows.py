@@ -83,6 +83,16 @@ def group_attn64():
     # enough (batch, head-group) CTAs for the four-heads-per-CTA tail kernel
     ok &= attn_case(160, 16, 257, 257, 64)
     ok &= attn_case(200, 12, 130, 130, 64)
+    # single-tile kernel (attention_small.cu): nq, nk <= 128 -- ragged sizes, cross shapes, one key, and enough
+    # (batch, head) problems for every slot of a persistent CTA to be reused several times
+    ok &= attn_case(1, 1, 1, 1, 64)
+    ok &= attn_case(2, 2, 17, 64, 64, self_attn=False)
+    ok &= attn_case(2, 2, 100, 33, 64, self_attn=False)
+    ok &= attn_case(3, 5, 65, 65, 64)
+    ok &= attn_case(2, 4, 128, 97, 64, self_attn=False)
+    ok &= attn_case(5, 16, 99, 99, 64, amp=4.0)
+    ok &= attn_case(256, 16, 99, 99, 64)
+    ok &= attn_case(97, 12, 99, 99, 64)
     return ok
 
 
