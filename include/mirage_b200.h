@@ -335,6 +335,39 @@ int mb_class_emb_grad(const int64_t* labels, const void* d_patches_bf16, float* 
                       int64_t batch, int64_t height, int64_t width, int32_t patch_h, int32_t patch_w,
                       int32_t n_classes, int32_t emb_dim, void* stream);
 
+/* Row-list forms of the two calls above (visible-token embedding, below): output / gradient row r belongs to
+ * source patch row_src[r] (= b * tokens_per_sample + token); a negative entry gives a zero row / is skipped. */
+int mb_semseg_patches_rows(const int64_t* labels, const void* class_emb_bf16, void* out, const int32_t* row_src,
+                           int64_t n_rows, int64_t batch, int64_t height, int64_t width, int32_t patch_h,
+                           int32_t patch_w, int32_t n_classes, int32_t emb_dim, void* stream);
+int mb_class_emb_grad_rows(const int64_t* labels, const void* d_patches_bf16, float* d_class_emb,
+                           const int32_t* row_src, int64_t n_rows, int64_t batch, int64_t height, int64_t width,
+                           int32_t patch_h, int32_t patch_w, int32_t n_classes, int32_t emb_dim, void* stream);
+
+/* Visible-token embedding of MIRAGEModel.forward with masking (mirage/model.py:352-356 input adapters + :384-391
+ * gather and global tokens): the masks are drawn from the token counts alone, so only the kept patches are
+ * projected.  Rows t = b * (n_keep + n_global) + j, the layout the encoder consumes.
+ *   mb_visible_rows      row_src [n_modalities, T] int32: source patch of row t for modality m, else -1;
+ *                        row_cls [T] int32: modality of row t, n_modalities + g for global token g, -1 for an id
+ *                        outside every modality.  starts / counts: HOST int32 [n_modalities] (first token of the
+ *                        modality in the concatenated sequence, tokens per sample).
+ *   mb_embed_rows_init   out[t] = bias_m + pos_m[token] | global_tokens[g] | 0  (f32 [T, dim]); bias / pos: HOST
+ *                        arrays of n_modalities DEVICE pointers (f32 [dim], f32 [count_m, dim] or NULL).
+ *   mb_gather_patches32  A[t] = the 32x32 patch of row_src[t] flattened (ph, pw) -- PatchedInputAdapter's Conv2d K
+ *                        order -- as f32 and/or bf16 [T, 1024] (either may be NULL); zero rows for negative entries.
+ *   mb_class_colsum      out[c] = sum of the rows of dy (f32 [T, dim]) whose row_cls is c (f32 [n_classes, dim]):
+ *                        bias gradients of the adapters and the global-token gradient in one pass. */
+int mb_visible_rows(const int64_t* ids_keep, int64_t batch, int64_t n_keep, int64_t n_global, int32_t n_modalities,
+                    const int32_t* starts, const int32_t* counts, int32_t* row_src, int32_t* row_cls, void* stream);
+int mb_embed_rows_init(const int32_t* row_src, const int32_t* row_cls, int32_t n_modalities, const int32_t* counts,
+                       const float* const* bias, const float* const* pos, const float* global_tokens, float* out,
+                       int64_t rows, int64_t dim, void* stream);
+int mb_gather_patches32(const float* images, const int32_t* row_src, float* a_f32, void* a_bf16, int64_t rows,
+                        int64_t height, int64_t width, void* stream);
+int64_t mb_class_colsum_workspace(int64_t rows, int64_t dim, int32_t n_classes);
+int mb_class_colsum(const float* dy, const int32_t* row_cls, float* out, void* workspace, int64_t rows, int64_t dim,
+                    int32_t n_classes, void* stream);
+
 /* SpatialOutputAdapter.get_queries_and_context (mirage/output_adapters.py:188-246), use_task_queries:
  *   queries[b, t] = (r < n_vis ? ctx[b, r] : mask_token) + emb[q_start + t],  r = ids_restore[b, q_start + t]
  *   context[b, j] = (r2 < n_vis ? ctx[b, r2] : mask_token) + emb[ids_keep[b, j]],  r2 = ids_restore[b, ids_keep[b, j]]

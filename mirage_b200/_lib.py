@@ -107,6 +107,8 @@ def _declare(lib):
     lib.mb_masked_loss_workspace.argtypes = [i64, i64, i64]
     lib.mb_optim_blocks.restype = C.c_int64
     lib.mb_optim_blocks.argtypes = [i64]
+    lib.mb_class_colsum_workspace.restype = C.c_int64
+    lib.mb_class_colsum_workspace.argtypes = [i64, i64, i32]
     for name in ("mb_layernorm_bwd_workspace", "mb_colsum_workspace", "mb_ln_meanpool_workspace"):
         getattr(lib, name).restype = C.c_int64
         getattr(lib, name).argtypes = [i64, i64]
@@ -132,6 +134,13 @@ SIGNATURES: dict[str, list] = {
     "mb_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "mb_semseg_patches": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
     "mb_class_emb_grad": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
+    "mb_semseg_patches_rows": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
+    "mb_class_emb_grad_rows": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
+    "mb_visible_rows": [_vp, _i64, _i64, _i64, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _vp],
+    "mb_embed_rows_init": [_vp, _vp, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _vp,
+                           _vp, _i64, _i64, _vp],
+    "mb_gather_patches32": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
+    "mb_class_colsum": [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp],
     "mb_dec_assemble_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp],
     "mb_dec_assemble_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
                             _i64, _vp],
@@ -156,7 +165,8 @@ SIGNATURES: dict[str, list] = {
 # every symbol include/mirage_b200.h declares
 EXPORTED = ["mb_last_error", "mb_version", "mb_sm_count", "mb_set_sm_reserve", "mb_set_pdl", "mb_clear_tensor_map_cache", "mb_gemm",
             "mb_attn_fwd", "mb_attn_bwd", "mb_attn_bwd_workspace", "mb_layernorm_bwd_workspace",
-            "mb_colsum_workspace", "mb_masked_loss_workspace", "mb_ln_meanpool_workspace", "mb_optim_blocks"]
+            "mb_colsum_workspace", "mb_masked_loss_workspace", "mb_ln_meanpool_workspace", "mb_optim_blocks",
+            "mb_class_colsum_workspace"]
 
 
 def lib():

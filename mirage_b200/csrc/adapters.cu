@@ -22,12 +22,20 @@ __device__ __forceinline__ void stf4(float* p, float4 v) { *reinterpret_cast<flo
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 semseg_patches_kernel(const long long* __restrict__ labels, const __nv_bfloat16* __restrict__ table,
-                      __nv_bfloat16* __restrict__ out, int H, int W, int P, int Q, int n_cls, int E) {
+                      __nv_bfloat16* __restrict__ out, int H, int W, int P, int Q, int n_cls, int E,
+                      const int* __restrict__ row_src) {
   extern __shared__ uint8_t sm[];
   __nv_bfloat16* s_tab = reinterpret_cast<__nv_bfloat16*>(sm);             // [n_cls * E]
   int* s_lab = reinterpret_cast<int*>(sm + ((n_cls * E * 2 + 15) & ~15));  // [P * Q]
   const int gw = W / Q, gh = H / P;
-  const int m = blockIdx.x;
+  // row list (visible-token embedding, visible.cu): output row blockIdx.x holds source patch row_src[blockIdx.x],
+  // or zeros when that is negative (a row that belongs to another modality)
+  const int m = row_src != nullptr ? row_src[blockIdx.x] : static_cast<int>(blockIdx.x);
+  if (m < 0) {
+    uint4* z = reinterpret_cast<uint4*>(out + (long long)blockIdx.x * E * P * Q);
+    for (int v = threadIdx.x; v < E * P * Q / 8; v += blockDim.x) z[v] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
   const int b = m / (gh * gw), t = m % (gh * gw);
   const int nh = t / gw, nw = t % gw;
   for (int i = threadIdx.x; i < n_cls * E; i += blockDim.x) s_tab[i] = table[i];
@@ -39,7 +47,7 @@ semseg_patches_kernel(const long long* __restrict__ labels, const __nv_bfloat16*
   __syncthreads();
   const int q8 = Q / 8;
   const int nvec = E * P * q8;
-  __nv_bfloat16* orow = out + (long long)m * E * P * Q;
+  __nv_bfloat16* orow = out + (long long)blockIdx.x * E * P * Q;
   for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
     const int c = v / (P * q8), r = v % (P * q8);
     const int ph = r / q8, pw0 = (r % q8) * 8;
@@ -61,7 +69,7 @@ semseg_patches_kernel(const long long* __restrict__ labels, const __nv_bfloat16*
 __global__ void __launch_bounds__(256)
 class_emb_grad_kernel(const long long* __restrict__ labels, const __nv_bfloat16* __restrict__ dA,
                       float* __restrict__ dE, int n_patches, int H, int W, int P, int Q, int n_cls,
-                      int E, int patches_per_block) {
+                      int E, int patches_per_block, const int* __restrict__ row_src) {
   extern __shared__ uint8_t sm[];
   const int PQ = P * Q;
   const int row_words = PQ / 2 + 1;                                   // bf16 pairs per channel row, +1 pad
@@ -74,7 +82,10 @@ class_emb_grad_kernel(const long long* __restrict__ labels, const __nv_bfloat16*
   const int quarter = warp >> 1;
   const int px0 = quarter * (PQ / 4), px1 = px0 + PQ / 4;
   const int m0 = blockIdx.x * patches_per_block;
-  for (int m = m0; m < min(m0 + patches_per_block, n_patches); ++m) {
+  for (int mo = m0; mo < min(m0 + patches_per_block, n_patches); ++mo) {
+    // row list: gradient row mo belongs to source patch row_src[mo] (negative: not of this modality, skip)
+    const int m = row_src != nullptr ? row_src[mo] : mo;
+    if (m < 0) continue;   // block-uniform
     const int b = m / (gh * gw), t = m % (gh * gw);
     const int nh = t / gw, nw = t % gw;
     __syncthreads();  // previous patch fully consumed (also orders the zero-fill)
@@ -83,7 +94,7 @@ class_emb_grad_kernel(const long long* __restrict__ labels, const __nv_bfloat16*
       long long l = labels[((long long)b * H + nh * P + ph) * W + nw * Q + pw];
       s_lab[i] = (int)(l < 0 ? 0 : (l >= n_cls ? n_cls - 1 : l));
     }
-    const uint4* arow = reinterpret_cast<const uint4*>(dA + (long long)m * E * PQ);
+    const uint4* arow = reinterpret_cast<const uint4*>(dA + (long long)mo * E * PQ);
     const int vec_per_row = PQ / 8;
     for (int v = threadIdx.x; v < E * vec_per_row; v += blockDim.x) {
       const int c = v / vec_per_row, j = v % vec_per_row;
@@ -259,16 +270,23 @@ extern "C" {
 int mb_semseg_patches(const int64_t* labels, const void* class_emb_bf16, void* out, int64_t batch,
                       int64_t height, int64_t width, int32_t patch_h, int32_t patch_w,
                       int32_t n_classes, int32_t emb_dim, void* stream) {
+  return mb_semseg_patches_rows(labels, class_emb_bf16, out, nullptr, 0, batch, height, width, patch_h, patch_w,
+                                n_classes, emb_dim, stream);
+}
+
+int mb_semseg_patches_rows(const int64_t* labels, const void* class_emb_bf16, void* out, const int32_t* row_src,
+                           int64_t n_rows, int64_t batch, int64_t height, int64_t width, int32_t patch_h,
+                           int32_t patch_w, int32_t n_classes, int32_t emb_dim, void* stream) {
   MB_REQUIRE(labels && class_emb_bf16 && out, "mb_semseg_patches: null pointer");
   MB_REQUIRE(patch_w % 8 == 0, "mb_semseg_patches: patch width must be a multiple of 8");
   MB_REQUIRE(height % patch_h == 0 && width % patch_w == 0, "mb_semseg_patches: ragged patches");
-  const long long m = batch * (height / patch_h) * (width / patch_w);
+  const long long m = row_src != nullptr ? n_rows : batch * (height / patch_h) * (width / patch_w);
   if (m == 0) return 0;
   const size_t smem = ((size_t)n_classes * emb_dim * 2 + 15 & ~(size_t)15) + (size_t)patch_h * patch_w * 4;
   semseg_patches_kernel<<<(unsigned)m, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(labels),
       reinterpret_cast<const __nv_bfloat16*>(class_emb_bf16), reinterpret_cast<__nv_bfloat16*>(out),
-      (int)height, (int)width, patch_h, patch_w, n_classes, emb_dim);
+      (int)height, (int)width, patch_h, patch_w, n_classes, emb_dim, row_src);
   MB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -276,11 +294,18 @@ int mb_semseg_patches(const int64_t* labels, const void* class_emb_bf16, void* o
 int mb_class_emb_grad(const int64_t* labels, const void* d_patches_bf16, float* d_class_emb,
                       int64_t batch, int64_t height, int64_t width, int32_t patch_h, int32_t patch_w,
                       int32_t n_classes, int32_t emb_dim, void* stream) {
+  return mb_class_emb_grad_rows(labels, d_patches_bf16, d_class_emb, nullptr, 0, batch, height, width, patch_h,
+                                patch_w, n_classes, emb_dim, stream);
+}
+
+int mb_class_emb_grad_rows(const int64_t* labels, const void* d_patches_bf16, float* d_class_emb,
+                           const int32_t* row_src, int64_t n_rows, int64_t batch, int64_t height, int64_t width,
+                           int32_t patch_h, int32_t patch_w, int32_t n_classes, int32_t emb_dim, void* stream) {
   MB_REQUIRE(labels && d_patches_bf16 && d_class_emb, "mb_class_emb_grad: null pointer");
   MB_REQUIRE(patch_w % 8 == 0, "mb_class_emb_grad: patch width must be a multiple of 8");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MB_CHECK_CUDA(cudaMemsetAsync(d_class_emb, 0, (size_t)n_classes * emb_dim * sizeof(float), st));
-  const long long m = batch * (height / patch_h) * (width / patch_w);
+  const long long m = row_src != nullptr ? n_rows : batch * (height / patch_h) * (width / patch_w);
   if (m == 0) return 0;
   MB_REQUIRE((patch_h * patch_w) % 8 == 0, "mb_class_emb_grad: patch area must be a multiple of 8");
   const int ppb = 16;
@@ -292,7 +317,7 @@ int mb_class_emb_grad(const int64_t* labels, const void* d_patches_bf16, float* 
   class_emb_grad_kernel<<<(unsigned)((m + ppb - 1) / ppb), 256, smem, st>>>(
       reinterpret_cast<const long long*>(labels),
       reinterpret_cast<const __nv_bfloat16*>(d_patches_bf16), d_class_emb, (int)m, (int)height,
-      (int)width, patch_h, patch_w, n_classes, emb_dim, ppb);
+      (int)width, patch_h, patch_w, n_classes, emb_dim, ppb, row_src);
   MB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -109,7 +109,7 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
 
   int bn;
   bool pair;
-  pick_tiling(a->m, a->n, a->k_splits, a->block_n, a->cta_pair, layout != LAY_KK_TF32, &bn, &pair);
+  pick_tiling(a->m, a->n, a->k_splits, a->block_n, a->cta_pair, true, &bn, &pair);
   MB_REQUIRE((pair && (bn == 256 || bn == 128)) || (!pair && (bn == 128 || bn == 64)),
              "mb_gemm: block_n=%d / cta_pair=%d is not an available tiling (pairs: 256|128, single: 128|64)",
              a->block_n, a->cta_pair);

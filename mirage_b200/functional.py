@@ -676,6 +676,94 @@ def semseg_embed(labels, class_emb, weight, bias, pos_rows, ph, pw):
 
 
 # ---------------------------------------------------------------------------------------------
+# Visible-token embedding (csrc/visible.cu): input adapters + torch.gather + global tokens of a masked forward
+# (mirage/model.py:352-356, :384-391) for the KEPT tokens only.  Returns what
+# token_gather(cat(adapter outputs), ids_keep, global_tokens) returns -- fp32 [B * (n_keep + n_glob), D] -- without
+# ever embedding the ~87 % of the patches the mask drops, in forward or in backward.
+#   meta: one dict per modality, in concatenation order:
+#     {'kind': 'patch32', 'count': tokens per sample, 'pos': fp32 [count, D] or None}            tensors: img, W, b
+#     {'kind': 'semseg',  'count': ..., 'pos': ..., 'ph': P_H, 'pw': P_W}                        tensors: labels, W, b, E
+# ---------------------------------------------------------------------------------------------
+class _EmbedVisible(Function):
+    @staticmethod
+    def forward(ctx, meta, ids_keep, global_tokens, need, *tensors):
+        n_mod = len(meta)
+        D = global_tokens.shape[-1]
+        n_glob = global_tokens.numel() // D
+        counts = [m['count'] for m in meta]
+        starts = [sum(counts[:i]) for i in range(n_mod)]
+        row_src, row_cls = ops.visible_rows(ids_keep, starts, counts, n_glob)
+        T = row_cls.numel()
+        per = []
+        k = 0
+        for m in meta:
+            n = 4 if m['kind'] == 'semseg' else 3
+            per.append(tensors[k:k + n])
+            k += n
+        tok = ops.embed_rows_init(row_src, row_cls, counts, [t[2].detach() for t in per], [m['pos'] for m in meta],
+                                  global_tokens.detach().reshape(n_glob, D).contiguous(), D)
+        twins = []
+        for i, (m, t) in enumerate(zip(meta, per)):
+            if m['kind'] == 'patch32':
+                a32, a16 = ops.gather_patches32(t[0], row_src[i], True, need)
+                ops.gemm(a32, t[1].detach().reshape(D, 1024), m=T, n=D, k=1024, residual=tok, out=tok)
+                twins.append(a16)
+            else:
+                a = ops.semseg_patches(t[0], bf16_weight(t[3]), m['ph'], m['pw'], row_src=row_src[i])
+                ops.gemm(a, bf16_weight(t[1]).reshape(D, -1), m=T, n=D, k=a.shape[1], residual=tok, out=tok)
+                twins.append(a)
+        if need:
+            ctx.meta, ctx.n_glob = meta, n_glob
+            ctx.n_tensors = [len(t) for t in per]
+            ctx.save_for_backward(row_src, row_cls, global_tokens, *[x for x in twins], *tensors)
+        return tok
+
+    @staticmethod
+    def backward(ctx, dtok):
+        meta, n_glob = ctx.meta, ctx.n_glob
+        n_mod = len(meta)
+        saved = ctx.saved_tensors
+        row_src, row_cls, global_tokens = saved[:3]
+        twins = saved[3:3 + n_mod]
+        tensors = saved[3 + n_mod:]
+        D = global_tokens.shape[-1]
+        dtok = dtok.contiguous()
+        dyb = _as_bf16(dtok)
+        cs = ops.class_colsum(dtok, row_cls, n_mod + n_glob)   # bias gradients + global-token gradient, one pass
+        grads = []
+        k = 0
+        for i, m in enumerate(meta):
+            n = ctx.n_tensors[i]
+            x, w, b = tensors[k], tensors[k + 1], tensors[k + 2]
+            tw = _sink_of(w)
+            dw = wgrad(dyb, twins[i], into=tw)
+            dw = _done(w, tw, dw if tw is not None else dw.reshape(w.shape))
+            tb = _sink_of(b)
+            if tb is not None:
+                tb.add_(cs[i])
+            db = _done(b, tb, cs[i])
+            grads += [None, dw, db]
+            if m['kind'] == 'semseg':
+                emb = tensors[k + 3]
+                if emb.requires_grad:
+                    d_a = dgrad(dyb, bf16_weight(w).reshape(D, -1))
+                    grads.append(ops.class_emb_grad(x, d_a, emb.shape[0], emb.shape[1], m['ph'], m['pw'],
+                                                    row_src=row_src[i]))
+                else:
+                    grads.append(None)
+            k += n
+        dglob = cs[n_mod:].reshape(global_tokens.shape) if global_tokens.requires_grad else None
+        return (None, None, dglob, None, *grads)
+
+
+def embed_visible(meta, tensors, ids_keep, global_tokens):
+    """-> fp32 [B * (n_keep + n_glob), D]; ``tensors``: per modality (x, weight, bias[, class_emb]) flattened."""
+    params = [t for t in tensors if t.is_floating_point()]
+    return _EmbedVisible.apply(meta, ids_keep.contiguous(), global_tokens, grad_needed(global_tokens, *params),
+                               *tensors)
+
+
+# ---------------------------------------------------------------------------------------------
 # fp32 -> bf16 cast as an autograd node (feeds a GEMM from an fp32 residual stream)
 # ---------------------------------------------------------------------------------------------
 class _ToBf16(Function):

@@ -85,6 +85,19 @@ class PatchedInputAdapter(nn.Module, _PosEmbMixin):
         return (C == 1 and self.P_H == 32 and self.P_W == 32 and x.dtype == torch.float32
                 and gw > 0 and 128 % gw == 0 and (gh * gw) % 128 == 0)
 
+    def visible_spec(self, x):
+        """Description of this modality for Fn.embed_visible (kept tokens only), or None when the fused path does
+        not cover the configuration (then MIRAGEModel.forward embeds every token and gathers, as the reference)."""
+        if x.dim() != 4 or not x.is_cuda:
+            return None
+        B, C, H, W = x.shape
+        if not (C == 1 and self.P_H == 32 and self.P_W == 32 and x.dtype == torch.float32 and H % 32 == 0
+                and W % 32 == 0) or self.pos_emb.requires_grad:
+            return None
+        nh, nw = H // 32, W // 32
+        meta = {'kind': 'patch32', 'count': nh * nw, 'pos': self._pos_rows(nh, nw, 'bicubic')}
+        return meta, (x.contiguous(), self.proj.weight, self.proj.bias)
+
     def write_tokens(self, x, out_buf, row_map):
         """No-autograd fast path: tokens of this modality written into rows
         ``b * stride + offset + t`` of ``out_buf`` ([B * stride, D] fp32)."""
@@ -173,6 +186,18 @@ class SemSegInputAdapter(nn.Module, _PosEmbMixin):
     @torch.jit.ignore
     def no_weight_decay(self):
         return {'pos_emb', 'class_emb'}
+
+    def visible_spec(self, x):
+        """See PatchedInputAdapter.visible_spec."""
+        if x.dim() != 3 or not x.is_cuda or x.dtype != torch.int64:
+            return None
+        B, H, W = x.shape
+        if self.P_W % 8 or H % self.P_H or W % self.P_W or self.pos_emb.requires_grad:
+            return None
+        nh, nw = H // self.P_H, W // self.P_W
+        meta = {'kind': 'semseg', 'count': nh * nw, 'pos': self._pos_rows(nh, nw, 'bilinear'),
+                'ph': self.P_H, 'pw': self.P_W}
+        return meta, (x.contiguous(), self.proj.weight, self.proj.bias, self.class_emb.weight)
 
     def write_tokens(self, x, out_buf, row_map):
         B, H, W = x.shape

@@ -13,6 +13,8 @@ vectorised row-gather kernel, and every Block is one fused autograd node (functi
 """
 from __future__ import annotations
 
+import os
+
 import itertools
 import math
 from collections import OrderedDict
@@ -68,6 +70,9 @@ class MIRAGEModel(nn.Module):
         # 'reference': the reference's torch op sequence (bit-exact masks given the same generators);
         # 'device': one fused sampling kernel (same distribution, own random stream; see set_mask_sampler)
         self.mask_sampler = 'reference'
+        # masked forward: embed the kept patches only (functional.embed_visible); MB_EMBED_VISIBLE=0 or
+        # model.visible_embedding = False restores embed-everything-then-gather
+        self.visible_embedding = os.environ.get('MB_EMBED_VISIBLE', '1') != '0'
         self._mask_rng = None
 
     # -- initialisation: same distributions as mirage/model.py:95-121 -----------------------------
@@ -316,18 +321,21 @@ class MIRAGEModel(nn.Module):
         """Input adapters -> (random | given) masking -> encoder -> output adapters.
         Returns ``(preds | encoder_tokens | features, task_masks)`` as mirage/model.py:305-431."""
         x = {'bscan': x} if isinstance(x, Tensor) else x
-        tokens_all, counts = self._embed_all(x)
-        B = tokens_all.shape[0]
+        counts = self._token_counts(x)
+        n_all = sum(counts.values())
+        B = next(iter(x.values())).shape[0]
         D = self.dim_tokens
         if self.input_info is None:
             self.input_info = self.generate_input_info(dict(counts), image_size=self.args.input_size)
         input_info = self.input_info
 
         if not mask_inputs:
-            num_encoded_tokens = sum(counts.values())
+            num_encoded_tokens = n_all
 
+        # The masks are drawn from the token COUNTS alone (model.py:168-239), so they can be sampled before the
+        # input adapters run -- and then only the kept patches need embedding (functional.embed_visible).
         if task_masks is None:
-            shapes = {d: tokens_all.new_empty((B, n, 0)) for d, n in counts.items()}
+            shapes = {d: self.global_tokens.new_empty((B, n, 0)) for d, n in counts.items()}
             task_masks, ids_keep, ids_restore = self.generate_random_masks(
                 shapes, num_encoded_tokens, alphas=alphas, sample_tasks_uniformly=sample_tasks_uniformly)
         else:
@@ -338,7 +346,16 @@ class MIRAGEModel(nn.Module):
             ids_keep = ids_shuffle[:, :(mask_all == 0).sum()]
 
         n_glob = self.num_global_tokens
-        tok = Fn.token_gather(tokens_all, ids_keep, self.global_tokens[0])     # [B, n_keep + n_glob, D]
+        specs = None
+        if self.visible_embedding and mask_inputs and 0 < ids_keep.shape[1] < n_all and n_glob > 0:
+            specs = [self.input_adapters[d].visible_spec(x[d]) if hasattr(self.input_adapters[d], 'visible_spec')
+                     else None for d in counts]
+        if specs is not None and all(sp is not None for sp in specs) and len(specs) <= 4:
+            tok = Fn.embed_visible([sp[0] for sp in specs], [t for sp in specs for t in sp[1]], ids_keep,
+                                   self.global_tokens).reshape(B, ids_keep.shape[1] + n_glob, D)
+        else:
+            tokens_all, counts = self._embed_all(x)
+            tok = Fn.token_gather(tokens_all, ids_keep, self.global_tokens[0])     # [B, n_keep + n_glob, D]
         N = tok.shape[1]
         x2 = tok.reshape(B * N, D)
 

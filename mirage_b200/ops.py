@@ -315,26 +315,99 @@ def attention_bwd(q, k, v, out, d_out, lse, dq, dk, dv, *, batch, heads, nq, nk,
         L.check(L.lib().mb_attn_bwd(C.byref(a), _stream()), "mb_attn_bwd")
 
 
-def semseg_patches(labels: torch.Tensor, class_emb_bf16: torch.Tensor, ph: int, pw: int) -> torch.Tensor:
-    """labels int64 [B,H,W] -> bf16 [B*(H/ph)*(W/pw), E*ph*pw] (embedding lookup + patch extraction)."""
-    _req_cuda(labels, class_emb_bf16)
+def semseg_patches(labels: torch.Tensor, class_emb_bf16: torch.Tensor, ph: int, pw: int,
+                   row_src: torch.Tensor | None = None) -> torch.Tensor:
+    """labels int64 [B,H,W] -> bf16 [B*(H/ph)*(W/pw), E*ph*pw] (embedding lookup + patch extraction).
+    ``row_src`` (int32 [T]): only these source patches, in this order (negative: zero row) -> bf16 [T, E*ph*pw]."""
+    _req_cuda(labels, class_emb_bf16, row_src)
     assert labels.dtype == torch.int64 and labels.is_contiguous()
     B, H, W = labels.shape
     n_cls, E = class_emb_bf16.shape
-    out = torch.empty((B * (H // ph) * (W // pw), E * ph * pw), dtype=torch.bfloat16, device=labels.device)
+    rows = B * (H // ph) * (W // pw) if row_src is None else row_src.numel()
+    out = torch.empty((rows, E * ph * pw), dtype=torch.bfloat16, device=labels.device)
     with _rec("semseg_patches", float(out.numel() * 2 + labels.numel() * 8), "byte"):
-        L.check(L.lib().mb_semseg_patches(labels.data_ptr(), class_emb_bf16.data_ptr(), out.data_ptr(),
-                                          B, H, W, ph, pw, n_cls, E, _stream()), "mb_semseg_patches")
+        L.check(L.lib().mb_semseg_patches_rows(labels.data_ptr(), class_emb_bf16.data_ptr(), out.data_ptr(),
+                                               _ptr(row_src), rows, B, H, W, ph, pw, n_cls, E, _stream()),
+                "mb_semseg_patches_rows")
     return out
 
 
-def class_emb_grad(labels, d_patches_bf16, n_cls: int, E: int, ph: int, pw: int) -> torch.Tensor:
-    _req_cuda(labels, d_patches_bf16)
+def class_emb_grad(labels, d_patches_bf16, n_cls: int, E: int, ph: int, pw: int,
+                   row_src: torch.Tensor | None = None) -> torch.Tensor:
+    """``row_src`` (int32 [T]): gradient row r belongs to source patch row_src[r] (negative: skipped)."""
+    _req_cuda(labels, d_patches_bf16, row_src)
     B, H, W = labels.shape
     out = torch.empty((n_cls, E), dtype=torch.float32, device=labels.device)
+    rows = 0 if row_src is None else row_src.numel()
     with _rec("class_emb_grad", float(d_patches_bf16.numel() * 2 + labels.numel() * 8), "byte", kernels=2):
-        L.check(L.lib().mb_class_emb_grad(labels.data_ptr(), d_patches_bf16.data_ptr(), out.data_ptr(),
-                                          B, H, W, ph, pw, n_cls, E, _stream()), "mb_class_emb_grad")
+        L.check(L.lib().mb_class_emb_grad_rows(labels.data_ptr(), d_patches_bf16.data_ptr(), out.data_ptr(),
+                                               _ptr(row_src), rows, B, H, W, ph, pw, n_cls, E, _stream()),
+                "mb_class_emb_grad_rows")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# visible-token embedding (csrc/visible.cu)
+# ---------------------------------------------------------------------------------------------
+def visible_rows(ids_keep: torch.Tensor, starts, counts, n_glob: int):
+    """ids_keep int64 [B, n_keep] -> (row_src int32 [n_mod, T], row_cls int32 [T]), T = B * (n_keep + n_glob)."""
+    _req_cuda(ids_keep)
+    assert ids_keep.dtype == torch.int64 and ids_keep.is_contiguous()
+    B, n_keep = ids_keep.shape
+    n_mod = len(starts)
+    T = B * (n_keep + n_glob)
+    row_src = torch.empty((n_mod, T), dtype=torch.int32, device=ids_keep.device)
+    row_cls = torch.empty((T,), dtype=torch.int32, device=ids_keep.device)
+    st = (C.c_int32 * n_mod)(*[int(v) for v in starts])
+    ct = (C.c_int32 * n_mod)(*[int(v) for v in counts])
+    with _rec("visible_rows", float(ids_keep.numel() * 8 + (n_mod + 1) * T * 4), "byte"):
+        L.check(L.lib().mb_visible_rows(ids_keep.data_ptr(), B, n_keep, n_glob, n_mod, st, ct, row_src.data_ptr(),
+                                        row_cls.data_ptr(), _stream()), "mb_visible_rows")
+    return row_src, row_cls
+
+
+def embed_rows_init(row_src: torch.Tensor, row_cls: torch.Tensor, counts, biases, pos_rows,
+                    global_tokens: torch.Tensor | None, dim: int) -> torch.Tensor:
+    """fp32 [T, dim]: bias_m + pos_m[token] on the rows of modality m, global token g on the global rows."""
+    _req_cuda(row_src, row_cls, global_tokens, *biases, *pos_rows)
+    n_mod, T = row_src.shape
+    out = torch.empty((T, dim), dtype=torch.float32, device=row_src.device)
+    ct = (C.c_int32 * n_mod)(*[int(v) for v in counts])
+    bp = (C.c_void_p * n_mod)(*[_ptr(b) for b in biases])
+    pp = (C.c_void_p * n_mod)(*[_ptr(p) for p in pos_rows])
+    for t in list(biases) + list(pos_rows) + [global_tokens]:
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    with _rec("embed_rows_init", float(2 * T * dim * 4), "byte"):
+        L.check(L.lib().mb_embed_rows_init(row_src.data_ptr(), row_cls.data_ptr(), n_mod, ct, bp, pp,
+                                           _ptr(global_tokens), out.data_ptr(), T, dim, _stream()),
+                "mb_embed_rows_init")
+    return out
+
+
+def gather_patches32(img: torch.Tensor, row_src: torch.Tensor, want_f32: bool = True, want_bf16: bool = False):
+    """img fp32 [B, 1, H, W]; row_src int32 [T] -> (fp32 [T, 1024] | None, bf16 [T, 1024] | None)."""
+    _req_cuda(img, row_src)
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.shape[1] == 1
+    H, W = img.shape[-2:]
+    T = row_src.numel()
+    a32 = torch.empty((T, 1024), dtype=torch.float32, device=img.device) if want_f32 else None
+    a16 = torch.empty((T, 1024), dtype=torch.bfloat16, device=img.device) if want_bf16 else None
+    with _rec("gather_patches32", float(T * 1024 * (4 + (4 if want_f32 else 0) + (2 if want_bf16 else 0))), "byte"):
+        L.check(L.lib().mb_gather_patches32(img.data_ptr(), row_src.data_ptr(), _ptr(a32), _ptr(a16), T, H, W,
+                                            _stream()), "mb_gather_patches32")
+    return a32, a16
+
+
+def class_colsum(dy: torch.Tensor, row_cls: torch.Tensor, n_classes: int) -> torch.Tensor:
+    """fp32 [n_classes, dim]: sums of the rows of dy (fp32 [T, dim]) by row class."""
+    _req_cuda(dy, row_cls)
+    assert dy.dtype == torch.float32 and dy.is_contiguous() and dy.dim() == 2
+    T, dim = dy.shape
+    out = torch.empty((n_classes, dim), dtype=torch.float32, device=dy.device)
+    ws = torch.empty(L.lib().mb_class_colsum_workspace(T, dim, n_classes), dtype=torch.uint8, device=dy.device)
+    with _rec("class_colsum", float(T * dim * 4), "byte", kernels=2):
+        L.check(L.lib().mb_class_colsum(dy.data_ptr(), row_cls.data_ptr(), out.data_ptr(), ws.data_ptr(), T, dim,
+                                        n_classes, _stream()), "mb_class_colsum")
     return out
 
 
