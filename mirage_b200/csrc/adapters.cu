@@ -206,31 +206,55 @@ __global__ void dec_assemble_bwd_emb_kernel(const float* __restrict__ dq, const 
   const int p = blockIdx.x;
   const int n_ctx = n_vis + n_glob;
   const bool in_task = (p >= q_start && p < q_start + n_q);
-  // eight samples per round: the index loads, then all gradient loads, are issued before any is consumed (the
-  // serial version -- index -> dependent row load -> add, 256 times per thread -- was latency-bound: 194 us for
-  // 93 MB at cfg 4); the summation order over b is unchanged
-  constexpr int U = 8;
+  // The batch loop is a chain of dependent loads (index -> gradient row) and was latency-bound (194 us for 93 MB
+  // at cfg 4, one column per thread, 256 samples in sequence).  Threads now own a float4 of columns, and the
+  // 256 / (Dd / 4) thread groups of the block take every G-th sample; the group partials are combined in group
+  // order through shared memory (fixed summation order).
+  __shared__ float4 s_acc[256], s_accm[256];
+  const int nvec = Dd / 4;
+  if (nvec <= 256 && 256 % nvec == 0 && blockDim.x == 256) {
+    const int G = 256 / nvec;
+    const int c4 = threadIdx.x % nvec, g = threadIdx.x / nvec;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), accm = acc;
+#pragma unroll 4
+    for (int b = g; b < B; b += G) {
+      const long long r = ids_restore[(long long)b * n_all + p];
+      const bool vis = (r >= 0 && r < n_vis);
+      if (in_task) {
+        const float4 q = ldf4(dq + ((long long)b * n_q + (p - q_start)) * Dd + c4 * 4);
+        acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        if (!vis) { accm.x += q.x; accm.y += q.y; accm.z += q.z; accm.w += q.w; }
+      }
+      if (vis) {
+        const float4 c = ldf4(dc + ((long long)b * n_ctx + r) * Dd + c4 * 4);
+        acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+      }
+    }
+    s_acc[threadIdx.x] = acc;
+    s_accm[threadIdx.x] = accm;
+    __syncthreads();
+    if (g == 0) {
+      for (int k = 1; k < G; ++k) {
+        const float4 a = s_acc[k * nvec + c4], m = s_accm[k * nvec + c4];
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        accm.x += m.x; accm.y += m.y; accm.z += m.z; accm.w += m.w;
+      }
+      stf4(demb + (long long)p * Dd + c4 * 4, acc);
+      if (in_task) stf4(dmask_part + (long long)(p - q_start) * Dd + c4 * 4, accm);
+    }
+    return;
+  }
   for (int col = threadIdx.x; col < Dd; col += blockDim.x) {
     float acc = 0.f, accm = 0.f;
-    for (int b0 = 0; b0 < B; b0 += U) {
-      long long r[U];
-      float g[U], c[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) r[u] = (b0 + u < B) ? ids_restore[(long long)(b0 + u) * n_all + p] : -1;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool live = b0 + u < B;
-        const bool vis = (r[u] >= 0 && r[u] < n_vis);
-        g[u] = (live && in_task) ? dq[((long long)(b0 + u) * n_q + (p - q_start)) * Dd + col] : 0.f;
-        c[u] = (live && vis) ? dc[((long long)(b0 + u) * n_ctx + r[u]) * Dd + col] : 0.f;
+    for (int b = 0; b < B; ++b) {
+      const long long r = ids_restore[(long long)b * n_all + p];
+      const bool vis = (r >= 0 && r < n_vis);
+      if (in_task) {
+        const float g = dq[((long long)b * n_q + (p - q_start)) * Dd + col];
+        acc += g;
+        if (!vis) accm += g;
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool vis = (r[u] >= 0 && r[u] < n_vis);
-        acc += g[u];
-        if (!vis) accm += g[u];
-        acc += c[u];
-      }
+      if (vis) acc += dc[((long long)b * n_ctx + r) * Dd + col];
     }
     demb[(long long)p * Dd + col] = acc;
     if (in_task) dmask_part[(long long)(p - q_start) * Dd + col] = accm;

@@ -33,6 +33,10 @@ int dispatch_gemm_pair_b(int bn, int layout, int epi, const CUtensorMap& ta, con
     return launch_gemm_pair<256, MB_A_PATCH32, 0, 4, 6>(ta, tb, p, stream);
   if (layout == LAY_PATCH_TF32 && bn == 128 && epi == 6)
     return launch_gemm_pair<128, MB_A_PATCH32, 0, 4, 6>(ta, tb, p, stream);
+  if (layout == LAY_KK_TF32 && bn == 256 && epi == 2)   // visible-token patch embedding: tok += A W^T (fp32, in place)
+    return launch_gemm_pair<256, MB_MAJOR_K, 0, 4, 2>(ta, tb, p, stream);
+  if (layout == LAY_KK_TF32 && bn == 128 && epi == 2)
+    return launch_gemm_pair<128, MB_MAJOR_K, 0, 4, 2>(ta, tb, p, stream);
   if (layout == LAY_KK_TF32 && bn == 256 && epi == 5)
     return launch_gemm_pair<256, MB_MAJOR_K, 0, 4, 5>(ta, tb, p, stream);
   if (layout == LAY_KK_TF32 && bn == 128 && epi == 5)
