@@ -480,7 +480,19 @@ def run_gpu(args):
     if world > 1:
         if args.nccl_max_ctas > 0:
             os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_max_ctas))
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces itself on stdout ("NCCL version ...") while the communicator is created; stdout carries
+        # exactly ONE JSON line, so file descriptor 1 points at stderr for the duration of the eager initialisation
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     # default invocation = both halves of BASELINE.json's metric: the MIRAGE-L encoder (headline line) and
     # the MultiMAE pretraining step (sub-record "pretrain"), plus the strong-scaling encoder point of SURVEY 8(d)

@@ -569,7 +569,10 @@ attn_tail_rows_kernel(const AttnDev p) {
   __shared__ float s_o[4][HD];
   pdl_sync();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
+  // CTAs walk the (batch, head) problems from the END: the tile kernel in front of this one finished with the last
+  // batches, whose K / V rows are the ones still in the 126 MB L2
+  const int bid = static_cast<int>(gridDim.x - 1 - blockIdx.x);
+  const int h = bid % p.H, b = bid / p.H;
   const __nv_bfloat16* kbase = p.k + static_cast<long long>(b) * p.Nk * p.ldk + h * HD;
   const __nv_bfloat16* vbase = p.v + static_cast<long long>(b) * p.Nk * p.ldv + h * HD;
 
@@ -652,7 +655,8 @@ attn_tail_rows4_kernel(const AttnDev p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hh = lane >> 3, c8 = (lane & 7) * 8;
   const int groups = p.H / 4;
-  const int h0 = (blockIdx.x % groups) * 4, b = blockIdx.x / groups;
+  const int bid = static_cast<int>(gridDim.x - 1 - blockIdx.x);   // most recently used K / V first (see above)
+  const int h0 = (bid % groups) * 4, b = bid / groups;
   const __nv_bfloat16* kbase = p.k + static_cast<long long>(b) * p.Nk * p.ldk + h0 * HD + lane * 8;
   const __nv_bfloat16* vbase = p.v + static_cast<long long>(b) * p.Nk * p.ldv + h0 * HD + lane * 8;
 

@@ -5,6 +5,8 @@
 //   visible-token gather / scatter       mirage/model.py:384-391
 //   bias gradient (column sums)          backward of every nn.Linear bias
 //   fp32 -> bf16 cast, global-token fill
+#include <cstdlib>
+
 #include "../../include/mirage_b200.h"
 #include "common.cuh"
 
@@ -25,10 +27,14 @@ __global__ void __launch_bounds__(kRowThreads)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ b, void* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, long long M, int D, long long ldx, long long ldy,
-                     float eps) {
+                     float eps, int reverse) {
   pdl_sync();
-  const long long row = (long long)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+  long long row = (long long)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
   if (row >= M) return;
+  // `reverse`: CTAs walk the rows from the END.  x was just written by a GEMM that walks its row tiles upwards,
+  // so the last ~100 MB of rows are still in the 126 MB L2 when this kernel starts -- and the GEMM that consumes
+  // y starts at row 0, i.e. with what this kernel wrote last.
+  if (reverse) row = M - 1 - row;
   const int lane = threadIdx.x & 31;
   const float* xr = x + row * ldx;
   float4 v[VPL];
@@ -90,7 +96,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ rstd_in, const float* __restrict__ dres,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
                      float* __restrict__ part, long long M, int D, long long ldx, long long lddy,
-                     long long lddx) {
+                     long long lddx, int reverse) {
   extern __shared__ float sred[];  // [8 warps][NS][D]
   constexpr int NS = DXSUM ? 3 : 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,8 +110,9 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
   }
   const float invD = 1.f / D;
   pdl_sync();
-  for (long long row = (long long)blockIdx.x * (kRowThreads / 32) + warp; row < M;
-       row += (long long)gridDim.x * (kRowThreads / 32)) {
+  for (long long r_ = (long long)blockIdx.x * (kRowThreads / 32) + warp; r_ < M;
+       r_ += (long long)gridDim.x * (kRowThreads / 32)) {
+    const long long row = reverse ? M - 1 - r_ : r_;   // see layernorm_fwd_kernel
     const float mean = mean_in[row], rstd = rstd_in[row];
     float4 xh[VPL], d[VPL];
     float s1 = 0.f, s2 = 0.f;
@@ -360,6 +367,16 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16
   *reinterpret_cast<uint2*>(out + i * 4) = pk;
 }
 
+// MB_ROW_REVERSE=0 restores ascending row order in the LayerNorm kernels (A/B switch)
+static int rows_reversed() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MB_ROW_REVERSE");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+
 template <bool OUT_BF16>
 static int launch_ln_fwd(const float* x, const float* w, const float* b, void* y, float* mean,
                          float* rstd, long long M, int D, long long ldx, long long ldy, float eps,
@@ -368,7 +385,7 @@ static int launch_ln_fwd(const float* x, const float* w, const float* b, void* y
 #define MB_LN(V)                                                                                   \
   case V:                                                                                          \
     MB_CHECK_CUDA(launch_row(layernorm_fwd_kernel<V, OUT_BF16>, dim3(grid), dim3(kRowThreads), 0, st, x, w, b, \
-                           y, mean, rstd, M, D, ldx, ldy, eps));                                   \
+                           y, mean, rstd, M, D, ldx, ldy, eps, rows_reversed()));                  \
     break;
   switch (D / 128) {
     MB_LN(1) MB_LN(2) MB_LN(3) MB_LN(4) MB_LN(5) MB_LN(6) MB_LN(7) MB_LN(8)
@@ -436,7 +453,7 @@ int mb_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const flo
       MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                          (int)smem));                                              \
     MB_CHECK_CUDA(launch_row(kern, dim3(grid), dim3(kRowThreads), smem, st, dy, x, weight, mean,     \
-                           rstd, dres, dx, dxb, part, rows, D, ldx, lddy, lddx));                  \
+                           rstd, dres, dx, dxb, part, rows, D, ldx, lddy, lddx, rows_reversed())); \
   }
 #define MB_LNB2(V)                                                                                 \
   case V:                                                                                          \
