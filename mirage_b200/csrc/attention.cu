@@ -761,6 +761,7 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
   p.q_pairs = (p.q_tiles + 1) / 2;
   p.kv_blocks = (p.Nk_main + 127) / 128;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.reverse = 0;
   {
     static int stagger = -1;
     if (stagger < 0) {
@@ -804,6 +805,7 @@ static int launch_attn_fwd(const mb_attn_args* a, cudaStream_t stream) {
     }
   }
   if (!main_done) {
+  note_direction(+1);   // the two-tile kernel walks the problems upwards
   CUtensorMap tq, tk, tv;
   {
     uint64_t dims[3] = {(uint64_t)a->heads * HD, (uint64_t)a->nq, (uint64_t)a->batch};

@@ -191,8 +191,9 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       // -------------------------------------------------------------- TMA producer
       int kv_count = 0, item_i = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i) {
-        const int quad = item % q_quads;
-        const int bh = item / q_quads;
+        const int ritem = p.reverse ? n_items - 1 - item : item;
+        const int quad = ritem % q_quads;
+        const int bh = ritem / q_quads;
         const int h = bh % p.H, b = bh / p.H;
         const int slot = item_i & 1;
         const uint32_t ph = (item_i >> 1) & 1;
@@ -476,8 +477,9 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     int item_i = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i) {
-      const int quad = item % q_quads;
-      const int bh = item / q_quads;
+      const int ritem = p.reverse ? n_items - 1 - item : item;
+      const int quad = ritem % q_quads;
+      const int bh = ritem / q_quads;
       const int h = bh % p.H, b = bh / p.H;
       if (p.k_tail > 0) mbar_wait(&q_full[item_i & 1], (item_i >> 1) & 1);
       const uint32_t v_tail_addr =
@@ -568,6 +570,7 @@ int launch_attn_fwd4(const mb_attn_args* a, const AttnDev& p_in, int poly, cudaS
   if (p_in.Nq_main <= 0 || p_in.Nq_main % (128 * kA4Groups) != 0) return 1;
   if (p_in.Nk_main < 2 * kA4Block || p_in.Nk_main % kA4Block != 0 || p_in.k_tail > kA4MaxTail) return 1;
   AttnDev p = p_in;
+  p.reverse = take_direction() < 0 ? 1 : 0;
   p.q_tiles = p.Nq_main / 128;
   p.kv_blocks = p.Nk_main / kA4Block;
   CUtensorMap tq, tk, tv;

@@ -481,6 +481,7 @@ static int launch_attn_bwd(const mb_attn_bwd_args* a, cudaStream_t stream) {
     MB_CHECK_CUDA(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   }
+  note_direction(+1);   // problems are walked upwards (take_direction(), common.cuh)
   const long long items = (long long)p.B * p.H;
   const long long grid = items < sm_count() ? items : sm_count();  // persistent CTAs
   MB_CHECK_CUDA(launch_k(kern, dim3((unsigned)grid), dim3(kAttnBwdThreads), Cfg::kSmemBytes, stream, tq, tk, tv, tdo,

@@ -29,6 +29,7 @@ struct AttnDev {
   int Nq_main, Nk_main, k_tail;
   int q_tiles, q_pairs, kv_blocks;
   int stagger;  // cycles softmax group 1 idles once at kernel start (anti-phases the two groups)
+  int reverse;  // (batch, head) problems are walked from the end (take_direction(), common.cuh); attention4 / _small
   float scale_log2;
 };
 

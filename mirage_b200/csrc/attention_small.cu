@@ -104,7 +104,8 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       // -------------------------------------------------------------- TMA producer (whole warp, uniform values)
       const bool leader = elect_one();
       for (int t = 0; t < n_local; ++t) {
-        const int item = static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x);
+        const int seq = static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x);
+        const int item = p.reverse ? n_items - 1 - seq : seq;
         const int h = item % p.H, b = item / p.H;
         const int s = t & (kASlots - 1);
         const uint32_t ph = (t / kASlots) & 1;
@@ -181,7 +182,8 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int nchunks = (nk + 31) >> 5;
 
     for (int t = s; t < n_local; t += kASlots) {
-      const int item = static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x);
+      const int seq = static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x);
+      const int item = p.reverse ? n_items - 1 - seq : seq;
       const int h = item % p.H, b = item / p.H;
       const uint32_t ph = (t / kASlots) & 1;
       mbar_wait(&s_full[s], ph);
@@ -273,8 +275,10 @@ attn_fwd_small_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 }
 
 // Fits: head_dim 64, one query tile, one key tile.  Returns 1 when the problem does not fit, < 0 on error.
-int launch_attn_fwd_small(const mb_attn_args* a, const AttnDev& p, cudaStream_t stream) {
+int launch_attn_fwd_small(const mb_attn_args* a, const AttnDev& p_in, cudaStream_t stream) {
   if (a->head_dim != 64 || a->nq > 128 || a->nk > 128) return 1;
+  AttnDev p = p_in;
+  p.reverse = take_direction() < 0 ? 1 : 0;
   CUtensorMap tq, tk, tv;
   {
     uint64_t dims[3] = {(uint64_t)a->heads * 64, (uint64_t)a->nq, (uint64_t)a->batch};

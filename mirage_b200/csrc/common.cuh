@@ -724,6 +724,16 @@ int make_tensor_map(CUtensorMap* out, const void* base, TmaDtype dtype, int rank
 // mb_set_sm_reserve() keeps free for concurrently running communication kernels (NCCL).
 int sm_count();
 
+// "Serpentine" row order between consecutive kernels.  Activations are 50 MB - 1 GB, the L2 holds 126 MB: a
+// consumer that walks its rows in the SAME direction as its producer finds nothing of what the producer wrote
+// (cyclic access over a buffer larger than an LRU cache), one that walks in the OPPOSITE direction starts with the
+// producer's last ~100 MB still on chip.  The library keeps the direction in which the most recent participating
+// kernel walked its rows; take_direction() flips it and returns the direction the kernel being launched must walk
+// (+1 upwards, -1 downwards); kernels with a fixed order call note_direction(+1).  Host-side state, one stream
+// assumed (as everywhere in this library); MB_SERPENTINE=0 makes every kernel walk upwards.
+int take_direction();
+void note_direction(int dir);
+
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  A kernel launched through launch_k() may start while its stream
 // predecessor is still draining: its CTAs become resident as SM resources free up and run their private

@@ -144,6 +144,14 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
   p.kb_per_split = (p.k_blocks + p.k_splits - 1) / p.k_splits;
   p.k_splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
   p.total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  // row direction: opposite to the producer of A for the token-major GEMMs; split-K (wgrad) walks the token
+  // dimension inside its K loop and keeps a fixed order
+  if (a->k_splits == 1 && !(a->epilogue & MB_EPI_ATOMIC) && a->a_layout == MB_MAJOR_K) {
+    p.m_reverse = take_direction() < 0 ? 1 : 0;
+  } else {
+    p.m_reverse = 0;
+    note_direction(+1);
+  }
   p.rows_per_img = 0;
   p.grid_w = 0;
   p.up_c = a->up_channels;

@@ -50,6 +50,7 @@ struct GemmDev {
   int epilogue;
   int m_tiles, n_tiles, k_blocks, k_splits, kb_per_split;
   int total_tiles;
+  int m_reverse;     // row tiles are walked downwards (see take_direction(), common.cuh)
   // MB_A_PATCH32
   int rows_per_img;  // tokens per image
   int grid_w;        // patches per image row
@@ -457,8 +458,9 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile) {
   const int tiles_mn = p.m_tiles * p.n_tiles;
   t.split = tile / tiles_mn;
   const int mn = tile - t.split * tiles_mn;
-  t.m_blk = mn / p.n_tiles;
-  t.n_blk = mn - t.m_blk * p.n_tiles;
+  const int mb = mn / p.n_tiles;
+  t.n_blk = mn - mb * p.n_tiles;
+  t.m_blk = p.m_reverse ? p.m_tiles - 1 - mb : mb;
   t.kb0 = t.split * p.kb_per_split;
   t.kb1 = min(t.kb0 + p.kb_per_split, p.k_blocks);
   return t;

@@ -367,15 +367,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16
   *reinterpret_cast<uint2*>(out + i * 4) = pk;
 }
 
-// MB_ROW_REVERSE=0 restores ascending row order in the LayerNorm kernels (A/B switch)
-static int rows_reversed() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MB_ROW_REVERSE");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v;
-}
+// row direction of the LayerNorm kernels: opposite to the producer of their input (take_direction(), common.cuh)
+static int rows_reversed() { return take_direction() < 0 ? 1 : 0; }
 
 template <bool OUT_BF16>
 static int launch_ln_fwd(const float* x, const float* w, const float* b, void* y, float* mean,

@@ -46,6 +46,21 @@ int sm_count() {
   return n < 2 ? 2 : n;
 }
 
+static int g_dir = +1;
+static int g_serpentine = -1;
+
+int take_direction() {
+  if (g_serpentine < 0) {
+    const char* e = getenv("MB_SERPENTINE");
+    g_serpentine = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (!g_serpentine) return +1;
+  g_dir = -g_dir;
+  return g_dir;
+}
+
+void note_direction(int dir) { g_dir = dir; }
+
 static int g_pdl = -1;
 
 int pdl_mode() {
