@@ -730,7 +730,11 @@ int sm_count();
 // producer's last ~100 MB still on chip.  The library keeps the direction in which the most recent participating
 // kernel walked its rows; take_direction() flips it and returns the direction the kernel being launched must walk
 // (+1 upwards, -1 downwards); kernels with a fixed order call note_direction(+1).  Host-side state, one stream
-// assumed (as everywhere in this library); MB_SERPENTINE=0 makes every kernel walk upwards.
+// assumed (as everywhere in this library).
+// Measured (profiles/r02_ab_experiments.txt): the full alternation is NEUTRAL against everything-upwards at cfg 2
+// and cfg 4, while reversing ONLY the LayerNorm kernels (GEMMs and attention upwards) gives +0.3-1.3 % -- so that
+// is the default, and MB_SERPENTINE=1 switches the full alternation on.
+bool serpentine_enabled();
 int take_direction();
 void note_direction(int dir);
 

@@ -367,8 +367,9 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16
   *reinterpret_cast<uint2*>(out + i * 4) = pk;
 }
 
-// row direction of the LayerNorm kernels: opposite to the producer of their input (take_direction(), common.cuh)
-static int rows_reversed() { return take_direction() < 0 ? 1 : 0; }
+// row direction of the LayerNorm kernels: downwards (their input was written by a GEMM walking upwards), or, with
+// MB_SERPENTINE=1, opposite to whatever the previous kernel did (take_direction(), common.cuh)
+static int rows_reversed() { return serpentine_enabled() ? (take_direction() < 0 ? 1 : 0) : 1; }
 
 template <bool OUT_BF16>
 static int launch_ln_fwd(const float* x, const float* w, const float* b, void* y, float* mean,

@@ -49,12 +49,16 @@ int sm_count() {
 static int g_dir = +1;
 static int g_serpentine = -1;
 
-int take_direction() {
+bool serpentine_enabled() {
   if (g_serpentine < 0) {
     const char* e = getenv("MB_SERPENTINE");
-    g_serpentine = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_serpentine = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
-  if (!g_serpentine) return +1;
+  return g_serpentine != 0;
+}
+
+int take_direction() {
+  if (!serpentine_enabled()) return +1;
   g_dir = -g_dir;
   return g_dir;
 }
