@@ -40,7 +40,7 @@ class GemmArgs(C.Structure):
         ("cta_pair", C.c_int32),
         ("colsum_out", C.c_void_p),
         ("twin_out", C.c_void_p), ("ld_twin", C.c_int64), ("row_stats", C.c_void_p),
-        ("ln_stats", C.c_void_p), ("ln_c1", C.c_void_p), ("ln_eps", C.c_float), ("pad_", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_c1", C.c_void_p), ("ln_eps", C.c_float), ("ln_parts", C.c_int32),
     ]
 
 
@@ -107,6 +107,8 @@ def _declare(lib):
     lib.mb_masked_loss_workspace.argtypes = [i64, i64, i64]
     lib.mb_optim_blocks.restype = C.c_int64
     lib.mb_optim_blocks.argtypes = [i64]
+    lib.mb_gemm_ln_parts.restype = C.c_int
+    lib.mb_gemm_ln_parts.argtypes = [i64, i64]
     lib.mb_class_colsum_workspace.restype = C.c_int64
     lib.mb_class_colsum_workspace.argtypes = [i64, i64, i32]
     for name in ("mb_layernorm_bwd_workspace", "mb_colsum_workspace", "mb_ln_meanpool_workspace"):
@@ -166,7 +168,7 @@ SIGNATURES: dict[str, list] = {
 EXPORTED = ["mb_last_error", "mb_version", "mb_sm_count", "mb_set_sm_reserve", "mb_set_pdl", "mb_clear_tensor_map_cache", "mb_gemm",
             "mb_attn_fwd", "mb_attn_bwd", "mb_attn_bwd_workspace", "mb_layernorm_bwd_workspace",
             "mb_colsum_workspace", "mb_masked_loss_workspace", "mb_ln_meanpool_workspace", "mb_optim_blocks",
-            "mb_class_colsum_workspace"]
+            "mb_class_colsum_workspace", "mb_gemm_ln_parts"]
 
 
 def lib():

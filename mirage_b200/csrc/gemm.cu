@@ -63,6 +63,13 @@ static void pick_tiling(long long m, long long n, int splits, int force_bn, int 
 
 using namespace mb200;
 
+extern "C" int mb_gemm_ln_parts(int64_t m, int64_t n) {
+  int bn;
+  bool pair;
+  pick_tiling(m, n, 1, 0, 0, true, &bn, &pair);
+  return static_cast<int>((n + bn / 2 - 1) / (bn / 2));
+}
+
 extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MB_REQUIRE(a != nullptr, "mb_gemm: null args");
@@ -127,6 +134,7 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
   p.ln_stats = a->ln_stats;
   p.ln_c1 = a->ln_c1;
   p.ln_eps = a->ln_eps;
+  p.ln_parts = a->ln_parts;
   p.M = (int)a->m;
   p.N = (int)a->n;
   p.K = (int)a->k;
@@ -203,10 +211,16 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
     MB_REQUIRE(!(a->twin_out && a->ln_stats), "mb_gemm: twin_out and ln_stats are mutually exclusive");
     if (a->twin_out) {
       MB_REQUIRE(a->residual && p.out_f32 && a->row_stats && !(a->epilogue & MB_EPI_GELU) && a->ld_twin % 8 == 0 &&
-                     (reinterpret_cast<uintptr_t>(a->twin_out) & 15) == 0,
+                     (reinterpret_cast<uintptr_t>(a->twin_out) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->row_stats) & 7) == 0,
                  "mb_gemm: twin_out needs the f32 residual epilogue, row_stats and a 16-byte aligned twin");
+      const int parts = static_cast<int>((a->n + bn / 2 - 1) / (bn / 2));
+      MB_REQUIRE(a->ln_parts == parts,
+                 "mb_gemm: row_stats laid out for %d partial sums per row, this tiling (block_n %d) produces %d -- "
+                 "size it with mb_gemm_ln_parts()", a->ln_parts, bn, parts);
       epi = EPI_RES_LN;
     } else {
+      MB_REQUIRE(a->ln_parts >= 1 && a->ln_parts <= 64, "mb_gemm: ln_parts %d out of range", a->ln_parts);
       MB_REQUIRE(a->ln_c1 && a->bias && !p.out_f32 && !a->residual && !a->aux_out &&
                      (reinterpret_cast<uintptr_t>(a->ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(a->ln_c1) & 15) == 0,
                  "mb_gemm: ln_stats needs ln_c1, bias, a bf16 output and no residual / aux_out");

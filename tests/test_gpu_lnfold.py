@@ -18,14 +18,21 @@ def test_lnfold_epilogues(T, D, N2):
     w = (torch.randn(D, D, device=dev, generator=g) * D ** -0.5).bfloat16()
     b = torch.randn(D, device=dev, generator=g) * 0.1
     res = torch.randn(T, D, device=dev, generator=g) * 2 + 0.3
-    stats = torch.zeros(2, T, 2, device=dev)[1]           # 8-byte aligned view, as the block path passes it
+    parts = ops.gemm_ln_parts(T, D)
+    stats = torch.full((2, T, parts, 2), float("nan"), device=dev)[1]   # every slot must be written (no zero-init)
     twin = torch.empty(T, D, dtype=torch.bfloat16, device=dev)
     out = ops.gemm(a, w, m=T, n=D, k=D, bias=b, residual=res, out_dtype=torch.float32, twin_out=twin, row_stats=stats)
     ref = a.float() @ w.float().t() + b + res
     assert (out - ref).abs().max().item() <= 1e-3
     assert torch.equal(twin, out.to(torch.bfloat16))
-    assert ((stats[:, 0] - out.sum(1)).abs().max() / out.sum(1).abs().max()).item() <= 1e-5
-    assert ((stats[:, 1] - (out * out).sum(1)).abs().max() / (out * out).sum(1).abs().max()).item() <= 1e-5
+    tot = stats.sum(1)
+    assert ((tot[:, 0] - out.sum(1)).abs().max() / out.sum(1).abs().max()).item() <= 1e-5
+    assert ((tot[:, 1] - (out * out).sum(1)).abs().max() / (out * out).sum(1).abs().max()).item() <= 1e-5
+    # deterministic: a second launch gives the same bits (the first version accumulated with atomics)
+    stats2 = torch.empty_like(stats)
+    ops.gemm(a, w, m=T, n=D, k=D, bias=b, residual=res, out_dtype=torch.float32, twin_out=torch.empty_like(twin),
+             row_stats=stats2)
+    assert torch.equal(stats, stats2)
     gamma = 1 + 0.1 * torch.randn(D, device=dev, generator=g)
     beta = 0.1 * torch.randn(D, device=dev, generator=g)
     w2 = torch.randn(N2, D, device=dev, generator=g) * D ** -0.5
