@@ -108,17 +108,18 @@ typedef struct mb_gemm_args {
   float* colsum_out; /* f32 [N] or NULL: ACCUMULATES the column sums of the stored output (the bias gradient
                         of the layer whose data gradient this GEMM produces); MB_EPI_DGELU with bf16 out only */
   /* LayerNorm folded into the GEMMs around it (inference path; Block.norm1 / norm2, mirage/utils.py:260-261):
-   *   producer  (residual GEMM, f32 out):  twin_out receives bf16(out) and row_stats[m][part] = {sum_n out, sum_n out^2}
-   *             over the part's columns (f32 [M, ln_parts, 2], every slot written, no atomics: deterministic) -- what the
-   *             following LayerNorm needs, without re-reading out;
+   *   producer  (residual GEMM, f32 out):  twin_out receives bf16(out) and row_stats[m][1 + part] = {sum_n out,
+   *             sum_n out^2} over the part's columns, then row_stats[m][0] = their sum in slot order (f32
+   *             [M, 1 + ln_parts, 2], every slot written, no atomics: deterministic) -- what the following LayerNorm
+   *             needs, without re-reading out;
    *   consumer  (A = that bf16 twin, B = bf16(gamma * W)):  out = rstd[m] * acc - rstd[m] * mean[m] * ln_c1[n] + bias[n]
-   *             with mean / rstd from ln_stats (f32 [M, ln_parts, 2] = the producer's row_stats, statistics over K = the
+   *             with mean / rstd from ln_stats[m][0] (f32 [M, 1 + ln_parts, 2] = the producer's row_stats, statistics over K = the
    *             LayerNorm width), ln_c1[n] = sum_k bf16(gamma_k W_nk), bias[n] = b[n] + sum_k beta_k W_nk;
    *             then GELU with MB_EPI_GELU.  Equals LayerNorm(x) W^T + b up to bf16 rounding. */
   void* twin_out;        /* bf16 [M, ld_twin] or NULL */
   int64_t ld_twin;
-  float* row_stats;      /* f32 [M, ln_parts, 2]; required with twin_out */
-  const float* ln_stats; /* f32 [M, ln_parts, 2] or NULL */
+  float* row_stats;      /* f32 [M, 1 + ln_parts, 2]; required with twin_out */
+  const float* ln_stats; /* f32 [M, 1 + ln_parts, 2] or NULL */
   const float* ln_c1;    /* f32 [N]; required with ln_stats */
   float ln_eps;
   int32_t ln_parts;      /* partial sums per row in row_stats / ln_stats: mb_gemm_ln_parts(m, n) of the PRODUCER GEMM */
@@ -126,7 +127,7 @@ typedef struct mb_gemm_args {
 
 int mb_gemm(const mb_gemm_args* args, void* stream);
 /* Number of partial sums per row the folded-LayerNorm producer epilogue writes for an [m, n] output with the tiling
- * mb_gemm picks for it (one per block_n / 2 columns); row_stats / ln_stats are f32 [m, parts, 2]. */
+ * mb_gemm picks for it (one per block_n / 2 columns); row_stats / ln_stats are f32 [m, 1 + parts, 2]. */
 int mb_gemm_ln_parts(int64_t m, int64_t n);
 
 /* ---------------------------------------------------------------- attention ---------------- */

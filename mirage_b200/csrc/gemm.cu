@@ -31,6 +31,21 @@ int dispatch_gemm_pair(int bn, int layout, int epi, const CUtensorMap& ta, const
 // pair tile is 256 rows over 2 SMs), so the per-SM work of one wave is proportional to BN.  Pair tiles
 // halve the B traffic per SM; the 1-CTA kernel is L2-operand-bound at BN=128 and shared-memory-bound at
 // BN=64, but offers twice as many, smaller tiles for problems that cannot fill 74 CTA pairs.
+// row_stats[m][0] = sum over the partial slots 1..parts, in slot order (deterministic; the epilogues never use atomics)
+__global__ void __launch_bounds__(256)
+ln_stats_reduce_kernel(float* __restrict__ stats, int M, int parts) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float2* sp = reinterpret_cast<float2*>(stats) + static_cast<long long>(row) * (parts + 1);
+  float2 t = sp[1];
+  for (int q = 2; q <= parts; ++q) {
+    const float2 v = sp[q];
+    t.x += v.x;
+    t.y += v.y;
+  }
+  sp[0] = t;
+}
+
 static void pick_tiling(long long m, long long n, int splits, int force_bn, int force_pair, bool pair_ok,
                         int* bn_out, bool* pair_out) {
   const int sms = sm_count();
@@ -277,6 +292,11 @@ extern "C" int mb_gemm(const mb_gemm_args* a, void* stream_) {
   if (ln_any) {
     const int rc_ln = dispatch_gemm_ln(bn, pair, epi, ta, tb, p, stream);
     MB_REQUIRE(rc_ln != 1, "mb_gemm: no folded-LayerNorm kernel for block_n %d, pair %d", bn, (int)pair);
+    if (rc_ln == 0 && epi == EPI_RES_LN) {
+      ln_stats_reduce_kernel<<<static_cast<unsigned>((a->m + 255) / 256), 256, 0, stream>>>(
+          a->row_stats, static_cast<int>(a->m), a->ln_parts);
+      MB_CHECK_CUDA(cudaGetLastError());
+    }
     return rc_ln;
   }
   int rc = pair ? dispatch_gemm_pair(bn, layout, epi, ta, tb, p, stream)

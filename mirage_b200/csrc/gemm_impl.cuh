@@ -43,7 +43,7 @@ struct GemmDev {
   const float* ln_stats;
   const float* ln_c1;
   float ln_eps;
-  int ln_parts;      // row statistics are kept as ln_parts partial sums per row (one per BN / 2 output columns)
+  int ln_parts;      // row statistics: [M][1 + ln_parts][2] = total, then one partial sum per BN / 2 output columns
   int M, N, K;
   long long ldc, ld_res, ld_aux;
   int res_period;
@@ -263,16 +263,9 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
     for (int it = 0; it < 8; ++it) {
       const int row = row_base + it * 4 + sub;
       float2 st = make_float2(0.f, 1.f);
-      if (row < p.M) {
-        // the producer's partial sums, added in slot order: deterministic (no atomics anywhere on the path)
-        const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(row) * p.ln_parts;
-        st = __ldg(sp);
-        for (int q = 1; q < p.ln_parts; ++q) {
-          const float2 t = __ldg(sp + q);
-          st.x += t.x;
-          st.y += t.y;
-        }
-      }
+      // slot 0 of the row = the producer's partial sums added in slot order by ln_stats_reduce_kernel (gemm.cu)
+      if (row < p.M)
+        st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(row) * (p.ln_parts + 1));
       const float mean = st.x * inv_k;
       const float var = fmaxf(st.y * inv_k - mean * mean, 0.f);
       ln_rstd[it] = rsqrtf(var + p.ln_eps);
@@ -450,7 +443,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmDev& p, uint32_t stage_a
       const int row = row_base + it * 4 + sub;
       const int part = n_base / (NSLABS * 32);   // this warp's column range = one slot of the row's statistics
       if (j4 == 0 && row < p.M && part < p.ln_parts)
-        *reinterpret_cast<float2*>(p.row_stats + 2ll * (static_cast<long long>(row) * p.ln_parts + part)) =
+        *reinterpret_cast<float2*>(p.row_stats + 2ll * (static_cast<long long>(row) * (p.ln_parts + 1) + 1 + part)) =
             make_float2(rs1[it], rs2[it]);
     }
   }

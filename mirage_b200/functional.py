@@ -546,7 +546,7 @@ def _block_infer_fold(x, B, N, heads, eps, n1w, n1b, qkv_w, qkv_b, proj_w, proj_
     c["src"] = c["twin"] = c["stats"] = None
     a = ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], batch=B, heads=heads, nq=N, nk=N,
                       head_dim=hd, scale=hd ** -0.5)
-    stats = torch.empty((2, T, ops.gemm_ln_parts(T, D), 2), dtype=torch.float32, device=dev)   # every slot is written
+    stats = torch.empty((2, T, 1 + ops.gemm_ln_parts(T, D), 2), dtype=torch.float32, device=dev)   # every slot is written
     x1b = torch.empty((T, D), dtype=torch.bfloat16, device=dev)
     x1 = ops.gemm(a, bf16_weight(proj_w), m=T, n=D, k=D, bias=proj_b, residual=x, out_dtype=torch.float32,
                   twin_out=x1b, row_stats=stats[0])

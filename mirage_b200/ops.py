@@ -138,15 +138,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int,
     if twin_out is not None:      # producer of a folded LayerNorm: bf16 twin of the output + row statistics
         assert row_stats is not None and twin_out.dtype == torch.bfloat16 and twin_out.stride(-1) == 1
         assert row_stats.dtype == torch.float32 and row_stats.is_contiguous() and row_stats.dim() == 3
-        assert row_stats.shape[0] == m and row_stats.shape[2] == 2     # [m, gemm_ln_parts(m, n), 2]
+        assert row_stats.shape[0] == m and row_stats.shape[2] == 2     # [m, 1 + gemm_ln_parts(m, n), 2]
         args.twin_out, args.ld_twin, args.row_stats = twin_out.data_ptr(), twin_out.stride(0), row_stats.data_ptr()
-        args.ln_parts = row_stats.shape[1]
+        args.ln_parts = row_stats.shape[1] - 1
     if ln_stats is not None:      # consumer: LayerNorm applied in the epilogue
         assert ln_c1 is not None and ln_stats.dtype == torch.float32 and ln_stats.is_contiguous()
         assert ln_stats.dim() == 3 and ln_stats.shape[0] == m and ln_stats.shape[2] == 2
         assert ln_c1.dtype == torch.float32 and ln_c1.is_contiguous() and bias is not None
         args.ln_stats, args.ln_c1, args.ln_eps = ln_stats.data_ptr(), ln_c1.data_ptr(), float(ln_eps)
-        args.ln_parts = ln_stats.shape[1]
+        args.ln_parts = ln_stats.shape[1] - 1
     if out_row_map is not None:
         args.out_row_period, args.out_row_stride, args.out_row_offset = out_row_map
     if unpatch is not None:

@@ -11,14 +11,14 @@ for (T, D, N2) in [(1026, 768, 2304), (4104, 1024, 4096), (300, 256, 1024)]:
     w = (torch.randn(D, D, device=dev) * D ** -0.5).bfloat16()
     b = torch.randn(D, device=dev) * 0.1
     res = torch.randn(T, D, device=dev) * 2 + 0.3
-    stats = torch.empty(T, ops.gemm_ln_parts(T, D), 2, device=dev)
+    stats = torch.empty(T, 1 + ops.gemm_ln_parts(T, D), 2, device=dev)
     twin = torch.empty(T, D, dtype=torch.bfloat16, device=dev)
     out = ops.gemm(a, w, m=T, n=D, k=D, bias=b, residual=res, out_dtype=torch.float32, twin_out=twin, row_stats=stats)
     ref = a.float() @ w.float().t() + b + res
     e_out = (out - ref).abs().max().item()
     e_twin = (twin.float() - out.to(torch.bfloat16).float()).abs().max().item()
-    e_s1 = ((stats.sum(1)[:, 0] - ref.sum(1)).abs().max() / ref.sum(1).abs().max()).item()
-    e_s2 = ((stats.sum(1)[:, 1] - (ref * ref).sum(1)).abs().max() / (ref * ref).sum(1).abs().max()).item()
+    e_s1 = ((stats[:, 0, 0] - ref.sum(1)).abs().max() / ref.sum(1).abs().max()).item()
+    e_s2 = ((stats[:, 0, 1] - (ref * ref).sum(1)).abs().max() / (ref * ref).sum(1).abs().max()).item()
     print(f"producer T={T} D={D}: out {e_out:.2e} twin {e_twin:.2e} sum {e_s1:.2e} sumsq {e_s2:.2e}")
     ok &= e_out < 2e-2 and e_twin == 0.0 and e_s1 < 1e-4 and e_s2 < 1e-4
     # consumer

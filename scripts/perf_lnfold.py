@@ -23,7 +23,7 @@ def t(fn, iters=20):
 a = torch.randn(T, D, device=dev).bfloat16()
 a4 = torch.randn(T, 4 * D, device=dev).bfloat16()
 res = torch.randn(T, D, device=dev)
-stats = torch.empty(T, ops.gemm_ln_parts(T, D), 2, device=dev)
+stats = torch.empty(T, 1 + ops.gemm_ln_parts(T, D), 2, device=dev)
 twin = torch.empty(T, D, dtype=torch.bfloat16, device=dev)
 b1 = torch.randn(D, device=dev)
 out32 = torch.empty(T, D, device=dev)

@@ -19,13 +19,14 @@ def test_lnfold_epilogues(T, D, N2):
     b = torch.randn(D, device=dev, generator=g) * 0.1
     res = torch.randn(T, D, device=dev, generator=g) * 2 + 0.3
     parts = ops.gemm_ln_parts(T, D)
-    stats = torch.full((2, T, parts, 2), float("nan"), device=dev)[1]   # every slot must be written (no zero-init)
+    stats = torch.full((2, T, 1 + parts, 2), float("nan"), device=dev)[1]   # every slot must be written (no zero-init)
     twin = torch.empty(T, D, dtype=torch.bfloat16, device=dev)
     out = ops.gemm(a, w, m=T, n=D, k=D, bias=b, residual=res, out_dtype=torch.float32, twin_out=twin, row_stats=stats)
     ref = a.float() @ w.float().t() + b + res
     assert (out - ref).abs().max().item() <= 1e-3
     assert torch.equal(twin, out.to(torch.bfloat16))
-    tot = stats.sum(1)
+    tot = stats[:, 0]
+    assert torch.allclose(tot, stats[:, 1:].sum(1), rtol=1e-5, atol=1e-3)
     assert ((tot[:, 0] - out.sum(1)).abs().max() / out.sum(1).abs().max()).item() <= 1e-5
     assert ((tot[:, 1] - (out * out).sum(1)).abs().max() / (out * out).sum(1).abs().max()).item() <= 1e-5
     # deterministic: a second launch gives the same bits (the first version accumulated with atomics)
