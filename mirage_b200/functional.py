@@ -504,11 +504,12 @@ class _Block(Function):
 # with this epilogue).  Accuracy is that of the unfolded bf16 path (checked with emulated roundings on the ViT-L
 # fp32 restatement incl. 30-sigma outlier channels: max-rel 6.8e-3 vs 7.3e-3, identical cosine; tests/test_gpu_lnfold.py).
 #
-# OFF by default (MB_LN_FOLD=1 or functional.LN_FOLD = True enables it).  Measured A/B inside one gpurun call at
-# cfg 2: 2814-2819 vs 2789 images/s (+1.0 %), although the standalone kernels say -150 us per block
-# (scripts/perf_lnfold.py): the step is power-capped, and the LayerNorm kernels were the low-power intervals in
-# which the clocks recovered.  For that 1 % the row statistics come from fp32 atomics, so identical images at
-# different batch positions no longer give bit-identical tokens (test_encoder_full_batch_properties).
+# OFF by default (MB_LN_FOLD=1 or functional.LN_FOLD = True enables it).  Measured A/B inside one gpurun call each
+# at cfg 2 (profiles/r02_ab_experiments.txt): with the row statistics accumulated by fp32 atomics +1.0 % -- but then
+# identical images at different batch positions stop giving bit-identical tokens; with the deterministic form kept
+# here (per-part partial sums written by the producer epilogue, added in slot order by a small kernel) -0.5 %.  The
+# standalone kernels say -150 us per block (scripts/perf_lnfold.py); the step does not follow because it is
+# power-capped and the LayerNorm kernels are its low-power intervals, in which the clocks recover.
 import os as _os
 LN_FOLD = _os.environ.get("MB_LN_FOLD", "0") == "1"
 _fold_cache: dict = {}
