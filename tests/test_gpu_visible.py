@@ -99,3 +99,47 @@ def test_masked_step_matches_embed_all_then_gather(size, B, n_keep):
             assert ga.norm().item() == 0.0, k
             continue
         assert (ga - gb).norm().item() <= 5e-2 * den, (k, (ga - gb).norm().item() / den)
+
+
+def test_ragged_modalities_no_grad():
+    """Two image modalities with different token counts (512 x 512 -> 256 tokens, 512 x 256 -> 128, pos-emb resized),
+    two global tokens, inference (no bf16 twins are built): kept-token embedding == embed-all-then-gather."""
+    from mirage_b200 import functional as Fn
+    from mirage_b200.input_adapters import PatchedInputAdapter
+    from mirage_b200.model import MIRAGEModel
+    from pretrain_case import pretrain_args
+    dev = torch.device("cuda:0")
+    mods = ["bscan", "slo"]
+    ins = {d: PatchedInputAdapter(num_channels=1, stride_level=1, patch_size_full=(32, 32), image_size=(512, 512))
+           for d in mods}
+    model = MIRAGEModel(pretrain_args(mods), input_adapters=ins, output_adapters=None, num_global_tokens=2,
+                        dim_tokens=128, depth=1, num_heads=2, drop_path_rate=0.0)
+    load_synth(model, seed=9)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(4)
+    B, n_keep = 5, 61
+    x = {"bscan": torch.rand(B, 1, 512, 512, generator=g).to(dev), "slo": torch.rand(B, 1, 512, 256, generator=g).to(dev)}
+    n_all = 256 + 128
+    ids_keep = torch.stack([torch.randperm(n_all, generator=g)[:n_keep] for _ in range(B)]).to(dev)
+    specs = [model.input_adapters[d].visible_spec(x[d]) for d in mods]
+    assert all(s is not None for s in specs) and [s[0]['count'] for s in specs] == [256, 128]
+    with torch.no_grad():
+        tok = Fn.embed_visible([s[0] for s in specs], [t for s in specs for t in s[1]], ids_keep, model.global_tokens)
+        all_tok, counts = model._embed_all(x)
+        ref = Fn.token_gather(all_tok, ids_keep, model.global_tokens[0]).reshape(tok.shape)
+    assert list(counts.values()) == [256, 128]
+    assert (tok - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
+    # and through MIRAGEModel.forward with the masks injected (both orders, encoder tokens)
+    mask_all = torch.ones(B, n_all, dtype=torch.long, device=dev)
+    mask_all.scatter_(1, ids_keep, 0)
+    ids_restore = torch.argsort(torch.cat([ids_keep, torch.zeros(B, 0, dtype=torch.long, device=dev)], 1), dim=1)
+    tm = dict(zip(mods, torch.split(mask_all, [256, 128], dim=1)))
+    model.generate_random_masks = lambda *a, **k: (tm, ids_keep, ids_restore)
+    outs = []
+    for vis in (True, False):
+        model.visible_embedding = vis
+        with torch.no_grad():
+            enc, _ = model(x, num_encoded_tokens=n_keep)
+        outs.append(enc.float())
+    assert outs[0].shape == (B, n_keep + 2, 128)
+    assert (outs[0] - outs[1]).abs().max().item() <= 2e-2 * outs[1].abs().max().item()
