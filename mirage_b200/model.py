@@ -347,7 +347,8 @@ class MIRAGEModel(nn.Module):
 
         n_glob = self.num_global_tokens
         specs = None
-        if self.visible_embedding and mask_inputs and 0 < ids_keep.shape[1] < n_all and n_glob > 0:
+        if (self.visible_embedding and mask_inputs and 0 < ids_keep.shape[1] < n_all and n_glob > 0
+                and len(counts) <= 4 and len(counts) + n_glob <= 8 and D <= 1024 and D % 4 == 0):   # limits of visible.cu
             specs = [self.input_adapters[d].visible_spec(x[d]) if hasattr(self.input_adapters[d], 'visible_spec')
                      else None for d in counts]
         if specs is not None and all(sp is not None for sp in specs) and len(specs) <= 4:
