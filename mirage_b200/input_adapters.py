@@ -160,8 +160,6 @@ class SemSegInputAdapter(nn.Module, _PosEmbMixin):
         self.emb_padding_idx = emb_padding_idx
         if self.emb_padding_idx is not None:
             self.num_classes += 1
-        if interpolate_class_emb:
-            raise NotImplementedError('interpolate_class_emb=True is not used by MIRAGE (mirage_wrapper.py:40)')
         self.P_H = max(1, self.patch_size_full[0] // stride_level)
         self.P_W = max(1, self.patch_size_full[1] // stride_level)
         if self.dim_tokens is not None:
@@ -180,16 +178,37 @@ class SemSegInputAdapter(nn.Module, _PosEmbMixin):
         self.class_emb = nn.Embedding(num_embeddings=self.num_classes, embedding_dim=self.dim_class_emb,
                                       padding_idx=self.emb_padding_idx)
         trunc_normal_(self.class_emb.weight, std=0.02)
-        self.proj = nn.Conv2d(in_channels=self.dim_class_emb, out_channels=self.dim_tokens,
-                              kernel_size=(self.P_H, self.P_W), stride=(self.P_H, self.P_W))
+        if self.interpolate_class_emb:
+            # reference input_adapters.py:194-200: bilinear DOWN-sampling of the embedded map by the patch size,
+            # then a 1x1 convolution (same state_dict keys: proj.1.weight / proj.1.bias)
+            self.proj = nn.Sequential(
+                nn.Upsample(scale_factor=(1 / self.P_H, 1 / self.P_W), mode='bilinear'),
+                nn.Conv2d(in_channels=self.dim_class_emb, out_channels=self.dim_tokens, kernel_size=1, stride=1))
+        else:
+            self.proj = nn.Conv2d(in_channels=self.dim_class_emb, out_channels=self.dim_tokens,
+                                  kernel_size=(self.P_H, self.P_W), stride=(self.P_H, self.P_W))
 
     @torch.jit.ignore
     def no_weight_decay(self):
         return {'pos_emb', 'class_emb'}
 
+    def _forward_interpolated(self, x):
+        """interpolate_class_emb=True (not used by any MIRAGE config): the embedding lookup and the bilinear
+        resampling are library calls, the 1x1 projection runs on the GEMM kernel."""
+        B, H, W = x.shape
+        nh, nw = H // self.P_H, W // self.P_W
+        e = self.class_emb(x).permute(0, 3, 1, 2)                      # [B, E, H, W]
+        e = self.proj[0](e)                                            # [B, E, nh, nw]
+        a = e.permute(0, 2, 3, 1).reshape(B * nh * nw, self.dim_class_emb)
+        conv = self.proj[1]
+        tok = Fn.linear(Fn.to_bf16(a.contiguous()), conv.weight.reshape(self.dim_tokens, self.dim_class_emb), conv.bias,
+                        out_f32=True)
+        pos = F.interpolate(self.pos_emb, size=(nh, nw), mode='bilinear')[0].flatten(1).t()
+        return (tok + pos.repeat(B, 1)).reshape(B, nh * nw, self.dim_tokens)
+
     def visible_spec(self, x):
         """See PatchedInputAdapter.visible_spec."""
-        if x.dim() != 3 or not x.is_cuda or x.dtype != torch.int64:
+        if x.dim() != 3 or not x.is_cuda or x.dtype != torch.int64 or self.interpolate_class_emb:
             return None
         B, H, W = x.shape
         if self.P_W % 8 or H % self.P_H or W % self.P_W or self.pos_emb.requires_grad:
@@ -202,6 +221,10 @@ class SemSegInputAdapter(nn.Module, _PosEmbMixin):
     def write_tokens(self, x, out_buf, row_map):
         B, H, W = x.shape
         nh, nw = H // self.P_H, W // self.P_W
+        if self.interpolate_class_emb:
+            n, stride, off = row_map
+            out_buf.view(B, stride, self.dim_tokens)[:, off:off + n].copy_(self._forward_interpolated(x))
+            return
         pos = self._pos_rows(nh, nw, 'bilinear')
         a = ops.semseg_patches(x, Fn.bf16_weight(self.class_emb.weight), self.P_H, self.P_W)
         ops.gemm(a, Fn.bf16_weight(self.proj.weight).reshape(self.dim_tokens, -1), m=a.shape[0],
@@ -215,6 +238,8 @@ class SemSegInputAdapter(nn.Module, _PosEmbMixin):
         assert (H % self.P_H == 0) and (W % self.P_W == 0), \
             f'Image sizes {H}x{W} must be divisible by patch sizes {self.P_H}x{self.P_W}'
         nh, nw = H // self.P_H, W // self.P_W
+        if self.interpolate_class_emb:
+            return self._forward_interpolated(x)
         pos = self._pos_rows(nh, nw, 'bilinear')
         tok = Fn.semseg_embed(x, self.class_emb.weight, self.proj.weight, self.proj.bias, pos,
                               self.P_H, self.P_W)

@@ -282,9 +282,28 @@ def gen_seg(ref_model, ref_in, ref_out):
     torch.save({"weights_seed": 31, "input_seed": 41, "batch": 2, "out": out}, GOLDEN / "seg.pt")
 
 
+def gen_semseg_interp(ref_in):
+    """SemSegInputAdapter(interpolate_class_emb=True) (mirage/input_adapters.py:194-200, :226-238): bilinear
+    down-sampling of the embedded class map + 1x1 projection; forward and the gradients of its parameters."""
+    with _quiet():
+        ad = ref_in.SemSegInputAdapter(num_classes=13, stride_level=1, patch_size_full=(8, 8), dim_tokens=128,
+                                       image_size=(128, 128), dim_class_emb=64, interpolate_class_emb=True)
+    sd = load_synth_into(ad, 17)
+    g = torch.Generator().manual_seed(23)
+    labels = torch.randint(0, 13, (2, 128, 128), generator=g)
+    out = ad(labels)
+    w = torch.randn(out.shape, generator=g)
+    (out * w).sum().backward()
+    grads = {k: p.grad.clone() for k, p in ad.named_parameters() if p.grad is not None}
+    torch.save({"state_dict": {k: v.clone() for k, v in sd.items()}, "labels": labels, "tokens": out.detach(),
+                "cotangent": w, "grads": grads}, GOLDEN / "semseg_interp.pt")
+    print("semseg_interp", tuple(out.shape), sorted(grads))
+
+
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    which = set(sys.argv[1:]) or {"encoder", "masks", "pretrain", "pretrain_large", "criterion", "cls", "cls_large", "seg"}
+    which = set(sys.argv[1:]) or {"encoder", "masks", "pretrain", "pretrain_large", "criterion", "cls", "cls_large", "seg",
+                                  "semseg_interp"}
     ref_hf, ref_model, ref_in, ref_out, ref_crit, ref_wrap = import_reference()
     torch.set_num_threads(8)
     if "encoder" in which:
@@ -303,5 +322,7 @@ if __name__ == "__main__":
         gen_cls(ref_wrap, ref_model, ref_in)
     if "seg" in which:
         gen_seg(ref_model, ref_in, ref_out)
+    if "semseg_interp" in which:
+        gen_semseg_interp(ref_in)
     if "cls_large" in which:        # BASELINE configs[4] at its real model size (ViT-L), batch 2
         gen_cls(ref_wrap, ref_model, ref_in, size="large", pools=("global",), fname="cls_large.pt")

@@ -96,6 +96,20 @@ def semseg_embed(labels: Tensor, class_emb: Tensor, weight: Tensor, bias: Tensor
     return tok + _tokens_from_posemb(pos_emb, nh, nw, "bilinear")
 
 
+def semseg_embed_interp(labels: Tensor, class_emb: Tensor, weight: Tensor, bias: Tensor, pos_emb: Tensor,
+                        patch: Tuple[int, int]) -> Tensor:
+    """SemSegInputAdapter.forward with interpolate_class_emb=True, mirage/input_adapters.py:194-200, :226-238:
+    the embedded class map is down-sampled bilinearly by the patch size (nn.Upsample(scale_factor=1/P),
+    align_corners=False) and projected by a 1x1 convolution.  weight [D, E, 1, 1]; returns [B, N, D]."""
+    B, H, W = labels.shape
+    D, E = weight.shape[:2]
+    nh, nw = H // patch[0], W // patch[1]
+    emb = class_emb[labels].permute(0, 3, 1, 2)                # [B, E, H, W]
+    small = F.interpolate(emb, scale_factor=(1 / patch[0], 1 / patch[1]), mode="bilinear")   # [B, E, nh, nw]
+    tok = small.permute(0, 2, 3, 1).reshape(B, nh * nw, E) @ weight.reshape(D, E).t() + bias
+    return tok + _tokens_from_posemb(pos_emb, nh, nw, "bilinear")
+
+
 # --------------------------------------------------------------------------------------------
 # transformer pieces
 # --------------------------------------------------------------------------------------------

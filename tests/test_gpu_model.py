@@ -248,3 +248,24 @@ def test_light_encoder_shapes_vs_oracle(mods, size, batch, image):
             assert len(layers) == len(refs)
             for a_, b_ in zip(layers, refs):
                 assert_parity(a_, b_, "return_all_layers")
+
+
+def test_semseg_adapter_interpolate_class_emb_vs_reference_golden():
+    """SemSegInputAdapter(interpolate_class_emb=True) (reference input_adapters.py:194-200): tokens and parameter
+    gradients against the fixture recorded from the unmodified reference."""
+    from pathlib import Path
+    from mirage_b200.input_adapters import SemSegInputAdapter
+    fx = torch.load(Path(__file__).parent / "golden" / "semseg_interp.pt")
+    dev = torch.device("cuda:0")
+    ad = SemSegInputAdapter(num_classes=13, stride_level=1, patch_size_full=(8, 8), dim_tokens=128,
+                            image_size=(128, 128), dim_class_emb=64, interpolate_class_emb=True)
+    ad.load_state_dict(fx["state_dict"])
+    ad = ad.to(dev).train()
+    tok = ad(fx["labels"].to(dev))
+    ref = fx["tokens"]
+    assert tok.shape == ref.shape
+    assert (tok.float().cpu() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    (tok * fx["cotangent"].to(dev)).sum().backward()
+    for k, g in fx["grads"].items():
+        mine = dict(ad.named_parameters())[k].grad.float().cpu()
+        assert (mine - g).norm().item() <= 5e-2 * g.norm().item(), k

@@ -196,3 +196,16 @@ def test_checkpoint_schema_round_trip(tmp_path):
         assert torch.equal(a, b), k
     s1, s2 = opt.state_dict()["state"], opt2.state_dict()["state"]
     assert s1.keys() == s2.keys() and all(torch.equal(s1[i]["exp_avg"], s2[i]["exp_avg"]) for i in s1)
+
+
+def test_semseg_interp_golden():
+    """SemSegInputAdapter(interpolate_class_emb=True): oracle restatement vs the reference's recorded tokens and
+    parameter gradients."""
+    fx = torch.load(GOLDEN / "semseg_interp.pt")
+    sd = {k: v.clone().requires_grad_(k != "pos_emb") for k, v in fx["state_dict"].items()}
+    tok = O.semseg_embed_interp(fx["labels"], sd["class_emb.weight"], sd["proj.1.weight"], sd["proj.1.bias"],
+                                sd["pos_emb"], (8, 8))
+    assert (tok - fx["tokens"]).abs().max().item() <= 1e-5 * fx["tokens"].abs().max().item()
+    (tok * fx["cotangent"]).sum().backward()
+    for k, g in fx["grads"].items():
+        assert (sd[k].grad - g).abs().max().item() <= 1e-4 * max(1e-6, g.abs().max().item()), k
