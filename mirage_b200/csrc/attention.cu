@@ -113,11 +113,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&s_free[g], 256);
-      mbar_init(&p_full[g], 256);
+      mbar_init(&s_free[g], 8);     // 8 softmax warps of the group, one elected arrival each
+      mbar_init(&p_full[g], 8);
       mbar_init(&o_full[g], 1);
       mbar_init(&o_free[g], 4);
-      mbar_init(&stats_full[g], 256);
+      mbar_init(&stats_full[g], 8);
     }
     mbar_fence_init();
   }
@@ -355,7 +355,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld_wait();
         }
         tc_fence_before();
-        mbar_arrive(&s_free[g]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[g]);   // one arrival per warp: 256 per-thread arrivals serialise on the word
 
         // local max over this half's columns (8 independent chains), then the row max across halves
         float mx_loc = -INFINITY;
@@ -441,7 +442,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_full[g]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
       }
 
       // row statistics for the epilogue warps (double-buffered by this group's item parity)
@@ -455,7 +457,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           for (int t = 0; t < kMaxTail; ++t) st[(3 + t) * 128 + r] = e_tail[t];
         }
       }
-      mbar_arrive(&stats_full[g]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stats_full[g]);
       ++ic;
     }
   } else {

@@ -79,10 +79,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* qdo_full = bars + 4;   // 2  TMA tx
   uint64_t* qdo_empty = bars + 6;  // 2  MMA commit after MMA2(t)
   uint64_t* sdp_full = bars + 8;   // MMA commit: S, dP of iteration t complete
-  uint64_t* sdp_free = bars + 9;   // 256 compute threads: S, dP copied to registers
-  uint64_t* pds_full = bars + 10;  // 256 compute threads: P, dS tiles written
+  uint64_t* sdp_free = bars + 9;   // 8 compute warps: S, dP copied to registers
+  uint64_t* pds_full = bars + 10;  // 8 compute warps: P, dS tiles written
   uint64_t* mma2_done = bars + 11; // MMA commit: dV, dK, dQ of iteration t complete, P/dS tiles free
-  uint64_t* acc_free = bars + 12;  // 128 drain threads: accumulators read out
+  uint64_t* acc_free = bars + 12;  // 4 drain warps: accumulators read out
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5;
@@ -105,10 +105,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&qdo_empty[s], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, 256);
-    mbar_init(pds_full, 256);
+    // one arrival per WARP (an elected lane behind __syncwarp): 256 + 256 + 128 per-thread arrivals per iteration
+    // serialise on three shared-memory words that all sit on the kernel's critical chain
+    mbar_init(sdp_free, 8);
+    mbar_init(pds_full, 8);
     mbar_init(mma2_done, 1);
-    mbar_init(acc_free, 128);
+    mbar_init(acc_free, 4);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -306,7 +308,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld_32x32b_x32_p(tmem_base + lane_off + 128 + half * 64 + 32, vd + 32);
           tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(sdp_free);  // MMA1(t+1) may overwrite S / dP now
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdp_free);  // MMA1(t+1) may overwrite S / dP now
           // P and dS in place: vs[e/2] <- packed P pair, vd[e/2] <- packed dS pair
           const float neg_lse = -lse2;
           const float ds_scale = p.scale;
@@ -333,7 +336,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(vd[c8 * 4], vd[c8 * 4 + 1], vd[c8 * 4 + 2], vd[c8 * 4 + 3]);
           }
           fence_proxy_async_smem();
-          mbar_arrive(pds_full);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pds_full);
         }
       }
     }
@@ -384,7 +388,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           for (int c = 0; c < HD / 32; ++c) tmem_ld_32x32b_x32_p(tmem_base + lane_off + 384 + c * 32, v + c * 32);
           tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(acc_free);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_free);
           if (row_ok) {
             const long long grow = static_cast<long long>(b) * p.Nq + qrow;
             if (kvb > 1) {
