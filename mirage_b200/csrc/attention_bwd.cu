@@ -135,26 +135,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // ---------------------------------------------------------------- TMA producer
       const bool leader = elect_one();
       int t = 0, jb = 0;
-      // The Q / dO / O slot of iteration t+2 is free only when MMA2(t) has retired, so its TMA load is issued about
-      // one iteration before it is needed -- less than the ~2.5k clk of HBM latency when an iteration is short (one
-      // 99 x 99 tile at cfg 4).  The tiles of iteration t+2 are therefore pulled into L2 while iteration t loads.
-      auto prefetch_iter = [&](int tt) {
-        const int per_item = kvb * qt;
-        const int item2 = static_cast<int>(blockIdx.x) + (tt / per_item) * static_cast<int>(gridDim.x);
-        if (item2 >= n_items) return;
-        const int within = tt % per_item;
-        const int j2 = within / qt, i2 = within - j2 * qt;
-        const int h2 = item2 % p.H, b2 = item2 / p.H;
-        if (leader) {
-          tma_prefetch_3d(&tm_q, h2 * HD, i2 * 128, b2);
-          tma_prefetch_3d(&tm_do, h2 * HD, i2 * 128, b2);
-          tma_prefetch_3d(&tm_o, h2 * HD, i2 * 128, b2);
-          if (i2 == 0) {
-            tma_prefetch_3d(&tm_k, h2 * HD, j2 * 128, b2);
-            tma_prefetch_3d(&tm_v, h2 * HD, j2 * 128, b2);
-          }
-        }
-      };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int h = item % p.H, b = item / p.H;
         for (int j = 0; j < kvb; ++j, ++jb) {
@@ -175,7 +155,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               tma_load_3d(smem + Cfg::kOffDO + qs * Cfg::kTileBytes, &tm_do, &qdo_full[qs], h * HD, i * 128, b);
               tma_load_3d(smem + Cfg::kOffO + qs * Cfg::kTileBytes, &tm_o, &qdo_full[qs], h * HD, i * 128, b);
             }
-            prefetch_iter(t + 2);
             __syncwarp();
           }
         }

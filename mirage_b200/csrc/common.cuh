@@ -267,14 +267,6 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-// L2 prefetch of a 3-D tile (no shared-memory destination, no completion tracking): the later tma_load_3d of the
-// same box then sees L2 latency instead of HBM latency
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int32_t c0, int32_t c1, int32_t c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
                                             int32_t c0, int32_t c1, int32_t c2, int32_t c3,
                                             int32_t c4) {
