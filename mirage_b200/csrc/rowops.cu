@@ -221,7 +221,7 @@ colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out0, fl
 template <bool IN_BF16>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const void* __restrict__ a, float* __restrict__ part, float* __restrict__ direct,
-                      long long M, int N, long long lda, int rows_per_block, int cpb) {
+                      long long M, int N, long long lda, int rows_per_block, int cpb, int reverse) {
   constexpr int EPC = IN_BF16 ? 8 : 4;  // elements per 16-byte chunk
   __shared__ float sm[256 * 8];
   pdl_sync();
@@ -229,7 +229,11 @@ colsum_partial_kernel(const void* __restrict__ a, float* __restrict__ part, floa
   const int cx = threadIdx.x % cpb, ly = threadIdx.x / cpb;
   const int chunk = blockIdx.y * cpb + cx;
   const int col = chunk * EPC;
-  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  // `reverse`: the first CTAs take the LAST row blocks -- the matrix (the qkv gradient attention-backward has just
+  // written upwards: 156 MB at cfg 4, more than the L2 holds) is then read starting with what is still on chip.
+  // Row block rb keeps its partial slot, so the result does not depend on the order.
+  const int rb = reverse ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
+  const long long row0 = (long long)rb * rows_per_block;
   const long long row1 = (row0 + rows_per_block < M) ? row0 + rows_per_block : M;
   float acc[8];
 #pragma unroll
@@ -284,7 +288,7 @@ colsum_partial_kernel(const void* __restrict__ a, float* __restrict__ part, floa
 #pragma unroll
       for (int e = 0; e < EPC; e += 4) red_add_v4(direct + col + e, t[e], t[e + 1], t[e + 2], t[e + 3]);
     } else {
-      float* o = part + (long long)blockIdx.x * N + col;
+      float* o = part + (long long)rb * N + col;
 #pragma unroll
       for (int e = 0; e < EPC; ++e) o[e] = t[e];
     }
@@ -507,12 +511,17 @@ int mb_colsum(const void* a, int32_t a_dtype, float* out, int32_t accumulate, vo
   float* part = reinterpret_cast<float*>(workspace);
   // accumulate into a 16-byte aligned destination: single kernel with vector reductions
   float* direct = (accumulate && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? out : nullptr;
+  static int rev = -1;   // MB_COLSUM_REVERSE=0: A/B switch
+  if (rev < 0) {
+    const char* e = getenv("MB_COLSUM_REVERSE");
+    rev = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
   if (a_dtype == MB_BF16)
     MB_CHECK_CUDA(launch_row(colsum_partial_kernel<true>, grid, dim3(256), 0, st, a, part, direct, rows, (int)cols, lda,
-                           rpb, cpb));
+                           rpb, cpb, rev));
   else
     MB_CHECK_CUDA(launch_row(colsum_partial_kernel<false>, grid, dim3(256), 0, st, a, part, direct, rows, (int)cols, lda,
-                           rpb, cpb));
+                           rpb, cpb, rev));
   if (direct != nullptr) return 0;
   MB_CHECK_CUDA(launch_row(colsum_final_kernel, dim3((unsigned)((cols + 31) / 32)), dim3(32, 32), 0, st, part, out,
                          nullptr, gx, (int)cols, (int)cols, accumulate, nullptr, 0));
